@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the mc3 sampling hot path (BASELINE.json metric: chain-steps/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (N=1 and per GPU at N>1, weak scaling): BASELINE config 2 -- DEMC,
+4096 chains per GPU, 5-parameter sinusoid+line model, 1e5 data points, fp64
+chi-squared with Gaussian priors.  A "step" is one generation: every chain of
+the population proposes, is evaluated against all data points and takes its
+Metropolis decision.
+
+One JSON line on stdout (rank 0):
+  value      chain-steps/s with inputs resident in HBM, CUDA-event time of
+             exactly K generations (one graph replay each), max over ranks
+  e2e        the same metric through the public hub call mcmc_driver.mcmc()
+             on HOST numpy inputs: H2D of the data, initial population, K
+             generations, report-point reads, D2H of the posterior and the
+             host post-statistics are all inside the timed region
+  roofline   the fused model+chi-squared kernel timed alone with CUDA events,
+             against the FP64 FMA peak measured live by mc3b_fma_peak
+  cpu_baseline  the oracle port of the reference loop (numpy model + the
+             reference's own C chi-squared from oracle/_ref when present) on
+             the host cores: a bounded sample of the same workload
+
+--impl reference prints the same line for the CPU reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NCHAINS_PER_GPU = 4096
+METRIC = 'chain-steps/s'
+
+
+# --------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '100', '-i', str(self.idx)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU reference arm / baseline: oracle port of the reference loop
+# --------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, nchains, gens, warm = args
+    import numpy as np
+    from oracle import mcmc as omc
+    from oracle import models as om
+    from oracle import kernels as ok
+    from oracle import ref
+    from mc3_b200 import workloads
+    w = workloads.config2()
+    chisq_fn, kind = ok.chisq, 'port'
+    if ref.have_ref_ext():
+        cs = ref.ref_ext()[0]
+
+        def chisq_fn(model, data, uncert, params, prior, plo, pup):   # stats.py:208-216
+            ip = (plo > 0) & (pup > 0)
+            return cs.chisq(model, data, uncert, (params - prior)[ip], plo[ip], pup[ip])
+        kind = 'reference-chisq'
+    kw = dict(nchains=nchains, sampler='demc', thinning=1, fepsilon=w['fepsilon'],
+              hsize=2, record=False, chisq_fn=chisq_fn, parent_seed=seed,
+              child_seed=seed + 1)
+    args = (w['data'], w['uncert'], om.sinusoid, w['params'], [w['x']], {},
+            w['pmin'], w['pmax'], w['pstep'], w['prior'], w['priorlow'], w['priorup'])
+    t_setup0 = time.perf_counter()
+    omc.mcmc(*args, nsamples=nchains*max(warm, 1), **kw)       # warm-up + setup cost
+    t_setup = time.perf_counter() - t_setup0
+    t0 = time.perf_counter()
+    omc.mcmc(*args, nsamples=nchains*(gens + max(warm, 1)), **kw)
+    t_all = time.perf_counter() - t0
+    return max(t_all - t_setup, 1e-9), kind
+
+
+def cpu_reference_run(steps, warmup, cores=None):
+    """Time `steps` generations of `cores` independent 7-chain DEMC populations
+    (one process each, the reference's own default chain count) at N=1e5."""
+    import multiprocessing as mp
+    cores = cores or max(1, (os.cpu_count() or 2) - 1)      # sampler_driver.py:336-341
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(1000 + 7*i, 7, steps, warmup) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    tmax = max(r[0] for r in res)
+    return dict(value=cores*7*steps/tmax, seconds=tmax, wall=wall, cores=cores,
+                kind=res[0][1], chain_steps=cores*7*steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    r = cpu_reference_run(K, W)
+    kind = 'port'
+    sample = (f'{r["cores"]} independent processes x 7 chains x {K} generations of config 2 '
+              f'(N=1e5, numpy sinusoid model) with the oracle port of mc3/chain.py; '
+              f'chi-squared by {"the reference C extension (oracle/_ref)" if r["kind"] != "port" else "the oracle C port"}')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': METRIC,
+        'n_gpus': args.gpus, 'steps': K, 'warmup': W,
+        'ms_per_step': 1e3*r['seconds']/K, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'config2: DEMC, 5-param sinusoid+line, N=1e5, fp64 chisq + Gaussian priors',
+                   'nchains': r['cores']*7, 'ndata': 100000, 'sampler': 'demc'},
+        'cpu_baseline': {'value': r['value'], 'unit': METRIC, 'cores': r['cores'],
+                         'kind': kind, 'sample': sample},
+        'e2e': {'value': r['value'], 'unit': METRIC, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+        'chisq_evals_per_s': r['value']*100000,
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mc3_b200 as mc3
+    from mc3_b200 import _lib, workloads
+    from mc3_b200.engine import Population
+    from mc3_b200.mcmc_driver import mcmc
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+    w = workloads.config2()
+    n = w['x'].size
+    nchains = NCHAINS_PER_GPU*world
+    model = mc3.models.BUILTIN[w['model']]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    pop = Population(w['data'], w['uncert'], model, w['params'], [w['x']], {},
+                     w['pstep'], w['pmin'], w['pmax'], w['prior'], w['priorlow'],
+                     w['priorup'], nchains=nchains, sampler=w['sampler'],
+                     fepsilon=w['fepsilon'], thinning=1, nzchain=W + K + 1, seed=1234,
+                     dtype=args.dtype, rank=rank, world=world)
+    pop.init_population('normal')
+    pop.run(W)                                   # warm-up (captures the generation graph)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = pop.launches
+    barrier()
+    for k in range(K):
+        flush.fill_(k & 0xFF)                    # evict L2 between timed steps (untimed)
+        ev[k][0].record()
+        pop.run(1)
+        ev[k][1].record()
+    barrier()
+    ck = clocks.stop() if rank == 0 else None
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    launches = pop.launches - launches0
+    value = nchains*K/(ms_total*1e-3)
+    acc = pop.counters()['numaccept']
+
+    # ---- roofline of the dominant kernel, timed alone -------------------
+    roof = None
+    if rank == 0:
+        import ctypes
+        P = pop.nextp[pop.chain0:pop.chain0 + pop.nlocal]
+        pop.data_chisq(P)
+        torch.cuda.synchronize(dev)
+        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(K)]
+        for k in range(K):
+            flush.fill_(k & 0xFF)
+            kev[k][0].record()
+            pop.data_chisq(P)
+            kev[k][1].record()
+        torch.cuda.synchronize(dev)
+        kms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+        flops = float(w['flops_per_point'])*pop.nlocal*n
+        # FP64 (or FP32) FMA peak, measured now on this GPU
+        sink = torch.zeros(8, dtype=torch.float64, device=dev)
+        fl = ctypes.c_double(0.0)
+        code = _lib.F64 if args.dtype == 'f64' else _lib.F32
+        best = 0.0
+        for it in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _lib.call('mc3b_fma_peak', code, 20000, sink.data_ptr(), ctypes.byref(fl),
+                      _lib.stream_ptr())
+            b.record()
+            torch.cuda.synchronize(dev)
+            if it:
+                best = max(best, fl.value/(a.elapsed_time(b)*1e-3))
+        achieved = flops/(kms*1e-3)
+        roof = {'bound': 'fp64' if args.dtype == 'f64' else 'fp32',
+                'kernel': 'k_model_chisq<SineModel>',
+                'achieved': achieved/1e12, 'peak': best/1e12, 'unit': 'TFLOP/s',
+                'frac': achieved/best, 'traffic': None,
+                'peak_source': 'measured live: mc3b_fma_peak register-resident FMA chains',
+                'ms_per_launch': kms,
+                'algorithmic_flops_per_chain_point': w['flops_per_point'],
+                'hbm_stream_GBs': 24.0*n/(kms*1e-3)/1e9,
+                'hbm_peak_GBs': _measured_peaks().get('hbm_gbs')}
+
+    # ---- end to end through the public hub call, host buffers ------------
+    barrier()
+    host = {k: np.array(w[k]) for k in ('data', 'uncert', 'x', 'params', 'pstep', 'pmin',
+                                       'pmax', 'prior', 'priorlow', 'priorup')}
+    quiet = mc3.Log(verb=-1)
+    t0 = time.perf_counter()
+    out = mcmc(host['data'], host['uncert'], model, host['params'], [host['x']], {},
+               host['pmin'], host['pmax'], host['pstep'], host['prior'],
+               host['priorlow'], host['priorup'], nchains, None, nchains*K,
+               w['sampler'], False, None, False, 0.0, 0.5, 0, 1, 1.0, w['fepsilon'],
+               10, 'normal', None, False, quiet, None, None, seed=77,
+               dtype=args.dtype, rank=rank, world=world)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    nfree = 5
+    h2d = 3*8*n + 8*10*8                                  # x, data, uncert + small vectors
+    d2h = out['posterior'].nbytes + out['log_post'].nbytes + out['zchain'].size*4
+    e2e = {'value': nchains*K/e2e_s, 'unit': METRIC,
+           'h2d_bytes_per_step': h2d/K, 'd2h_bytes_per_step': d2h/K,
+           'seconds': e2e_s,
+           'includes': 'H2D of data, initial population (10 x nchains evaluations), '
+                       'K generations, report reads, D2H of posterior, host post-statistics'}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_run(args.cpu_steps, 1)
+        cpu = {'value': r['value'], 'unit': METRIC, 'cores': r['cores'], 'kind': 'port',
+               'sample': f'{r["cores"]} processes x 7 chains x {args.cpu_steps} generations '
+                         f'of the same workload (N=1e5) with the oracle port of the '
+                         f'reference loop, numpy model, chi-squared by '
+                         f'{"oracle/_ref (reference C)" if r["kind"] != "port" else "oracle C port"}; '
+                         f'{r["seconds"]:.1f} s'}
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world,
+            'steps': K, 'warmup': W, 'ms_per_step': ms_total/K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': args.dtype, 'data': 'synthetic',
+            'config': {'workload': w['name'], 'nchains': nchains,
+                       'nchains_per_gpu': NCHAINS_PER_GPU, 'ndata': n,
+                       'sampler': w['sampler'], 'model': w['model'],
+                       'l2': 'flushed between timed steps (256 MB write, untimed)',
+                       'parallelism': f'chains partitioned over {world} GPU(s); '
+                                      'NCCL all-gather of the population per generation'
+                                      if world > 1 else 'single GPU'},
+            'chisq_evals_per_s': value*n,
+            'acceptance_rate_pct': 100.0*acc/(nchains*(W + K)),
+            'e2e': e2e, 'gpu_launches': launches, 'clocks': ck,
+            'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--cpu-steps', type=int, default=100)
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,261 @@
+/* mc3b200.h -- C ABI of libmc3b200.so, the B200 (sm_100a) replacement for the
+ * native layer of pcubillos/mc3 and for the per-iteration loop that sits on it.
+ *
+ * Every entry point returns an int status (MC3B_OK on success); the message of
+ * the last failure on the calling thread is available from mc3b_last_error().
+ * All pointers are DEVICE pointers unless a parameter is marked [host].  The
+ * caller owns every buffer; the library allocates nothing persistent.
+ * `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls
+ * are asynchronous with respect to the host and re-entrant per stream.
+ *
+ * Reference interfaces replaced (paths relative to the reference root):
+ *   _chisq.chisq / _chisq.residuals         src_c/_chisq.c:37-79, 111-140
+ *   stats.h priors()                        src_c/include/stats.h:90-109
+ *   _dwt.chisq / _dwt.daub4                 src_c/_dwt.c:56-119, 154-186
+ *   _time_averaging.binrms                  src_c/_time_averaging.c:55-143
+ *   _binarray.binarray                      src_c/_binarray.c:34-81
+ *   Chain.run() proposal / Metropolis loop  mc3/chain.py:183-299
+ *   Chain.eval_model()                      mc3/chain.py:302-340
+ *   gelman_rubin()                          mc3/stats/gelman.py:12-92
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference adds.
+ */
+#ifndef MC3B200_H
+#define MC3B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MC3B_VERSION 100            /* 0.1.0 */
+
+enum { MC3B_OK = 0, MC3B_ERR_ARG = 1, MC3B_ERR_CUDA = 2 };
+enum { MC3B_F64 = 0, MC3B_F32 = 1 };
+enum { MC3B_MODEL_POLYNOMIAL = 0, MC3B_MODEL_SINUSOID = 1,
+       MC3B_MODEL_GAUSSIAN = 2, MC3B_MODEL_BOX = 3 };
+enum { MC3B_MRW = 0, MC3B_DEMC = 1, MC3B_SNOOKER = 2 };
+
+#define MC3B_MAX_PARS 32            /* parameters per model vector          */
+#define MC3B_MAX_SPLIT 4096         /* data splits of one chi-squared launch */
+
+int mc3b_version(void);
+const char* mc3b_last_error(void);
+/* Number of SMs of the current device (sizes grids); <0 on error. */
+int mc3b_device_sms(void);
+
+/* ------------------------------------------------------------------------
+ * Chi-squared family   (replaces _chisq.c and Chain.eval_model)
+ * ---------------------------------------------------------------------- */
+
+/* Choose the launch shape of mc3b_model_chisq for (nchains, n): writes the
+ * number of data splits (rows of the `partial` workspace) to *nsplit.
+ * Deterministic function of its arguments. */
+int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit);
+
+/* Fused built-in model + data chi-squared, batched over chains:
+ *   partial[s, c] = sum over the points i of split s of
+ *                   ((model(params[c], x_i) - data_i) * invsig_i)^2
+ * params   [nchains, ldp] fp64, row c = FULL parameter vector of chain c; the
+ *          model sees its first `nmodel` entries (chain.py:316-319: with the
+ *          wavelet likelihood the model gets params[0:-3]).
+ * x, data, invsig  [n] fp64 (dtype F64) or fp32 (dtype F32); invsig = 1/uncert.
+ * partial  [nsplit, ldpartial] fp64 workspace (ldpartial >= nchains), nsplit
+ *          from mc3b_model_chisq_plan; entry [s, c] belongs to row c of params.
+ * The sum over splits and the prior terms are added by mc3b_chisq_finish or,
+ * inside the sampler, by mc3b_metropolis. */
+int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
+                     int64_t nchains, int nmodel, const void* x,
+                     const void* data, const void* invsig, int64_t n,
+                     double* partial, int64_t ldpartial, int nsplit,
+                     void* stream);
+
+/* model[c, i] = model(params[c], x_i), fp64, out is [nchains, n] row-major. */
+int mc3b_model_eval(int model_id, const double* params, int64_t ldp,
+                    int64_t nchains, int nmodel, const double* x, int64_t n,
+                    double* out, void* stream);
+
+/* chisq[c] = sum_s partial[s*ldpartial + c] (fixed order s = 0..nsplit-1)
+ *          + sum over j with priorlow_j > 0 and priorup_j > 0 of
+ *            ((p_cj - prior_j) / (p_cj > prior_j ? priorup_j : priorlow_j))^2
+ * (mc3/stats/stats.py:208-216 + stats.h:90-109).  prior* may be NULL. */
+int mc3b_chisq_finish(const double* partial, int64_t ldpartial, int nsplit,
+                      int64_t nchains,
+                      const double* params, int64_t ldp, int npars,
+                      const double* prior, const double* priorlow,
+                      const double* priorup, double* chisq, void* stream);
+
+/* _chisq.chisq for models evaluated elsewhere (user callables):
+ *   chisq[c] = sum_i ((model[c, i] - data_i) / uncert_i)^2, model [nchains, ldm]. */
+int mc3b_chisq_batch(const double* model, int64_t ldm, int64_t nchains,
+                     const double* data, const double* uncert, int64_t n,
+                     double* chisq, void* stream);
+
+/* _chisq.residuals: out[i] = (model_i - data_i)/uncert_i, i < n; then the np
+ * prior terms off_k / (off_k > 0 ? up_k : low_k).  off may be NULL (np = 0). */
+int mc3b_residuals(const double* model, const double* data,
+                   const double* uncert, int64_t n, const double* off,
+                   const double* low, const double* up, int64_t np,
+                   double* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Sampler   (replaces the body of Chain.run, mc3/chain.py:183-299)
+ * ---------------------------------------------------------------------- */
+
+/* Population state.  Per-chain arrays are indexed by GLOBAL chain id and have
+ * `nchains` entries on every device; a device only touches its own slice
+ * [chain0, chain0 + nlocal). */
+typedef struct mc3b_sampler {
+    int64_t nchains, chain0, nlocal;
+    int32_t npars, nfree, sampler, reflect;   /* reflect: 0 = reject out-of-bounds (reference) */
+    const int32_t* ifree;        /* [nfree] indices of free parameters            */
+    const double* pstep;         /* [npars] >0 free, 0 fixed, <0 shared (-(k+1))  */
+    const double* pmin;          /* [npars]                                        */
+    const double* pmax;          /* [npars]                                        */
+    const double* params0;       /* [npars] template: values of fixed parameters   */
+    const double* prior;         /* [npars] or NULL                                */
+    const double* priorlow;      /* [npars] or NULL                                */
+    const double* priorup;       /* [npars] or NULL                                */
+    double gamma;                /* fgamma * 2.38 / sqrt(2 nfree)  chain.py:175    */
+    double fepsilon;
+    uint64_t seed;               /* Philox key                                     */
+    double* X;                   /* [nchains, nfree] current states (freepars)     */
+    double* chisq_cur;           /* [nchains] chi-squared of X                     */
+    double* Z;                   /* [zlen, nfree] history (reference layout)       */
+    double* log_post;            /* [zlen]                                         */
+    int32_t* zchain;             /* [zlen]                                         */
+    int64_t zlen, M0;
+    double* nextp;               /* [nchains, npars] proposed full vectors         */
+    double* mrfactor;            /* [nchains] snooker Metropolis factor            */
+    double* u;                   /* [nchains] Metropolis uniform                   */
+    int32_t* inb;                /* [nchains] 1 = proposal within bounds           */
+    int32_t* naccept;            /* [nchains] accepted proposals                   */
+    int32_t* outbounds;          /* [nfree] out-of-bound counts (chain.py:242)     */
+    double* best_chisq;          /* [nchains] lowest accepted chi-squared          */
+    double* best_x;              /* [nchains, nfree] its free parameters           */
+    int64_t* best_gen;           /* [nchains] generation where it was reached      */
+    int64_t* gen_dev;            /* device generation counter (graph mode) or NULL */
+    int64_t thinning;            /* generations per history row (graph mode)       */
+} mc3b_sampler_t;
+
+/* Recorded random stream of one generation (replay mode), indexed by global
+ * chain id; produced by the oracle's draw recorder from the reference's numpy
+ * stream.  a/b: snooker iR1,iR2 or demc r1,r2 after the reference's fix-ups. */
+typedef struct mc3b_draws {
+    const double* normal;        /* [nfree] shared support draw (chain.py:185) */
+    const int64_t* a;
+    const int64_t* b;
+    const int64_t* iz;           /* snooker jump: z row, -1 = none               */
+    const double* usj;           /* snooker: uniform tested against 0.1          */
+    const double* gs;            /* snooker jump: U(1.2, 2.2)                    */
+    const double* u;             /* Metropolis uniform                           */
+} mc3b_draws_t;
+
+/* Proposal for generation `gen`, chains [c_begin, c_end) of this device's
+ * slice (global ids): draws (Philox, keyed by seed/chain/generation), jump
+ * (chain.py:195-232), nextp = X + jump, bounds test with outbounds counters
+ * (chain.py:235-243), shared-parameter fill (chain.py:246-247), snooker
+ * Metropolis factor (chain.py:251-255) and the Metropolis uniform.  zsize is
+ * the number of history rows a snooker draw may use.  [host] s. */
+int mc3b_propose(const mc3b_sampler_t* s, int64_t gen, int64_t zsize,
+                 int64_t c_begin, int64_t c_end, void* stream);
+
+/* Device-driven generations (so one captured CUDA graph can be replayed):
+ * pass gen < 0 to mc3b_propose / mc3b_metropolis and they read the generation
+ * g from *s->gen_dev and derive, for the lock-step history layout,
+ *   zsize = M0 + (g / thinning) * nchains
+ *   zrow0 = M0 + ((g+1)/thinning - 1) * nchains  if (g+1) % thinning == 0, else -1.
+ * mc3b_advance increments *s->gen_dev (one thread) at the end of a generation. */
+int mc3b_advance(const mc3b_sampler_t* s, void* stream);
+
+/* Same, with every random number taken from `d` instead of Philox.  [host] s, d */
+int mc3b_propose_replay(const mc3b_sampler_t* s, const mc3b_draws_t* d,
+                        int64_t c_begin, int64_t c_end, void* stream);
+
+/* Metropolis step for chains [c_begin, c_end): chisq* of chain c = sum over s of
+ * partial[s*ldpartial + (c - c_off)] (fixed order) + priors; accept iff exp(0.5 (chisq - chisq*)) * mrfactor > u
+ * (chain.py:257-274); update X, chisq_cur, naccept, per-chain best; when
+ * zrow0 >= 0 write the thinned sample of chain c to history row zrow0 + c
+ * (chain.py:276-289).  [host] s. */
+int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial,
+                    int64_t ldpartial, int nsplit, int64_t c_off, int64_t gen,
+                    int64_t zrow0, int64_t c_begin, int64_t c_end, void* stream);
+
+/* Trial points of the initial population (mcmc_driver.py:229-262):
+ * trial[t, :] = params0 with free entries drawn N(params0, pstep) (kickoff 0)
+ * or U(pmin, pmax) (kickoff 1), shared parameters filled; ok[t] = 1 when all
+ * parameters are inside [pmin, pmax].  Trial t uses Philox counter
+ * (t, slot, round, 0xFFFFFFFF).  [host] s. */
+int mc3b_init_trials(const mc3b_sampler_t* s, int kickoff, int64_t ntrials,
+                     int64_t round, double* trial, int32_t* ok, void* stream);
+
+/* Gelman-Rubin PSRF per free parameter (gelman.py:36-92) over samples
+ * k = burnin .. burnin+niter-1 of every chain; sample k of chain c is history
+ * row  rows[c*ldr + k]  when rows != NULL, else  M0 + k*nchains + c  (the
+ * lock-step layout).  work: [2, nchains, nfree] fp64.  psrf: [nfree]. */
+int mc3b_gelman_rubin(const double* Z, int64_t nfree, int64_t nchains,
+                      int64_t M0, const int64_t* rows, int64_t ldr,
+                      int64_t burnin, int64_t niter, double* work, double* psrf,
+                      void* stream);
+
+/* ------------------------------------------------------------------------
+ * Wavelet likelihood   (replaces _dwt.c + wavelet.h)
+ * ---------------------------------------------------------------------- */
+
+/* Bytes of workspace mc3b_dwt_chisq needs for (nchains, n). */
+int64_t mc3b_dwt_workspace(int64_t nchains, int64_t n);
+
+/* Carter & Winn (2009) wavelet pseudo chi-squared, batched over chains, for
+ * n = 2^k >= 4 only (the reference is undefined elsewhere):
+ * residual = data - model, D4 pyramid, per-scale sums, log terms
+ * (_dwt.c:71-118).  gamma, sigma_r, sigma_w are params[c, npars-3 .. npars-1].
+ * Model: built-in (model_id >= 0, evaluated from params[c, 0..nmodel) on x) or
+ * given (model_id < 0, `model` is [nchains, ldm]).  Priors are NOT added here
+ * (use mc3b_chisq_finish with nsplit = 1 or mc3b_metropolis). */
+int mc3b_dwt_chisq(int model_id, const double* params, int64_t ldp,
+                   int64_t nchains, int npars, int nmodel, const double* x,
+                   const double* model, int64_t ldm, const double* data,
+                   int64_t n, void* workspace, double* chisq, void* stream);
+
+/* _dwt.daub4: forward (isign >= 0) or inverse (isign < 0) D4 transform of a
+ * length-n2 array, n2 = 2^k >= 4; workspace holds n2 doubles; in and out
+ * must not alias.  Zero padding to 2^k is the caller's (stats.dwt_daub4 does it). */
+int mc3b_daub4(const double* in, int64_t n2, int isign, void* workspace,
+               double* out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Time-series diagnostics   (replace _time_averaging.c and _binarray.c)
+ * ---------------------------------------------------------------------- */
+
+/* Bytes of workspace for mc3b_binrms on n points. */
+int64_t mc3b_binrms_workspace(int64_t n, int64_t maxbins, int64_t binstep);
+
+/* _time_averaging.binrms: for bin sizes b = 1, 1+binstep, ... <= maxbins:
+ * rms of the bin means, its lower/upper errors (asymptotic for more than 35
+ * bins, inverse-gamma credible region otherwise), the Gaussian extrapolation
+ * stderr and b.  Outputs have (maxbins-1)/binstep + 1 entries. */
+int mc3b_binrms(const double* data, int64_t n, int64_t maxbins,
+                int64_t binstep, void* workspace, double* rms, double* rmslo,
+                double* rmshi, double* stderr_, double* binsz, void* stream);
+
+/* _binarray.binarray: n/binsize bin means; with uncert != NULL, 1/sigma^2
+ * weighted means and binstd = sqrt(1/sum(1/sigma^2)) (binstd may be NULL
+ * otherwise). */
+int mc3b_binarray(const double* data, int64_t n, int64_t binsize,
+                  const double* uncert, double* bindata, double* binstd,
+                  void* stream);
+
+/* ------------------------------------------------------------------------
+ * Roofline denominators
+ * ---------------------------------------------------------------------- */
+
+/* Register-resident FMA chains on every SM: runs `iters` dependent FMAs per
+ * accumulator; *flops receives the flop count of the launch (2 per FMA).
+ * Time it with events to get the FP64 / FP32 pipe peak. */
+int mc3b_fma_peak(int dtype, int64_t iters, double* sink, double* flops /*[host]*/,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MC3B200_H */

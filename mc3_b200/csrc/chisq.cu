@@ -1,0 +1,334 @@
+// mc3_b200 -- chi-squared family (replaces src_c/_chisq.c and the model +
+// chi-squared half of Chain.eval_model, mc3/chain.py:302-340).
+//
+// k_model_chisq is the hot kernel of the sampler: one launch evaluates the
+// built-in model and the data chi-squared of EVERY chain of the population.
+//
+//   grid  = (chain groups, data splits); block = 4 warps.
+//   warp  = LC chains x LP = 32/LC point lanes.  LC = 32: one chain per lane,
+//           every lane walks all points of a tile (shared-memory broadcast);
+//           LC = 8 / 1: fewer chains, lanes share the points of the tile.
+//   data  = x, data, 1/sigma tiles of TILE points, staged into shared memory
+//           by 1-D TMA bulk copies (cp.async.bulk + mbarrier, 3 stages), so a
+//           tile is fetched once per CTA and serves all its chains; the
+//           per-chain constants live in registers for the whole launch.
+//   sum   = per lane in registers, then a fixed-order xor-shuffle over the
+//           point lanes, one partial per (split, chain): deterministic.
+//
+// Bound: FP64 (or FP32) pipe -- nchains*F flops per 24 bytes of data.
+#include "models.cuh"
+
+namespace {
+
+constexpr int WARPS = 4;
+constexpr int STAGES = 3;
+template <typename T> struct tilecfg { static constexpr int TILE = 256; };
+template <> struct tilecfg<float> { static constexpr int TILE = 512; };
+
+template <typename T> struct ChisqArgs {
+    const double* params;
+    int64_t ldp, nchains;
+    const T *x, *d, *w;
+    int64_t n;
+    double* partial;
+    int64_t ldpartial;
+    int use_tma;
+};
+
+template <class M, typename T, int LC, int CPT>
+__global__ void __launch_bounds__(WARPS * 32) k_model_chisq(ChisqArgs<T> a) {
+    constexpr int TILE = tilecfg<T>::TILE;
+    constexpr int LP = 32 / LC;
+    __shared__ __align__(128) T sx[STAGES][TILE];
+    __shared__ __align__(128) T sd[STAGES][TILE];
+    __shared__ __align__(128) T sw[STAGES][TILE];
+    __shared__ __align__(8) uint64_t bar[STAGES];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lc = lane % LC, lp = lane / LC;
+    const int64_t cbase = ((int64_t)blockIdx.x * WARPS + warp) * (LC * CPT) + lc;
+
+    M mdl[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        int64_t c = cbase + (int64_t)k * LC;
+        if (c >= a.nchains) c = a.nchains - 1;      // idle lanes shadow the last chain
+        mdl[k].load(a.params + c * a.ldp);
+    }
+    double acc[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; k++) acc[k] = 0.0;
+
+    // Tiles of this split: balanced contiguous ranges of FULL tiles; the
+    // ragged tail (n % TILE points) belongs to the last split.
+    const int64_t nfull = a.n / TILE;
+    const int64_t tb = nfull * blockIdx.y / gridDim.y, te = nfull * (blockIdx.y + 1) / gridDim.y;
+    const int64_t nt = te - tb;
+
+    if (a.use_tma) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < STAGES; s++) mbar_init(&bar[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        auto issue = [&](int64_t t, int s) {
+            const int64_t off = t * TILE;
+            mbar_expect_tx(&bar[s], 3u * TILE * sizeof(T));
+            bulk_g2s(sx[s], a.x + off, TILE * sizeof(T), &bar[s]);
+            bulk_g2s(sd[s], a.d + off, TILE * sizeof(T), &bar[s]);
+            bulk_g2s(sw[s], a.w + off, TILE * sizeof(T), &bar[s]);
+        };
+        if (threadIdx.x == 0)
+            for (int s = 0; s < STAGES && s < nt; s++) issue(tb + s, s);
+        for (int64_t it = 0; it < nt; it++) {
+            const int s = (int)(it % STAGES);
+            mbar_wait(&bar[s], (uint32_t)((it / STAGES) & 1));
+            T tacc[CPT];
+#pragma unroll
+            for (int k = 0; k < CPT; k++) tacc[k] = (T)0;
+#pragma unroll 4
+            for (int i = lp; i < TILE; i += LP) {
+                const T x = sx[s][i], d = sd[s][i], w = sw[s][i];
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const T r = (mdl[k].eval(x) - d) * w;
+                    tacc[k] = fma(r, r, tacc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++) acc[k] += (double)tacc[k];
+            __syncthreads();                    // everyone is done reading stage s
+            if (threadIdx.x == 0 && it + STAGES < nt) issue(tb + it + STAGES, s);
+        }
+    } else {
+        for (int64_t it = 0; it < nt; it++) {   // unaligned inputs: plain staged loads
+            const int64_t off = (tb + it) * TILE;
+            __syncthreads();
+            for (int i = threadIdx.x; i < TILE; i += WARPS * 32) {
+                sx[0][i] = a.x[off + i]; sd[0][i] = a.d[off + i]; sw[0][i] = a.w[off + i];
+            }
+            __syncthreads();
+            T tacc[CPT];
+#pragma unroll
+            for (int k = 0; k < CPT; k++) tacc[k] = (T)0;
+            for (int i = lp; i < TILE; i += LP) {
+                const T x = sx[0][i], d = sd[0][i], w = sw[0][i];
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    const T r = (mdl[k].eval(x) - d) * w;
+                    tacc[k] = fma(r, r, tacc[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++) acc[k] += (double)tacc[k];
+        }
+    }
+
+    // Ragged tail, straight from global memory (last split only).
+    if (blockIdx.y == gridDim.y - 1) {
+        T tacc[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; k++) tacc[k] = (T)0;
+        for (int64_t i = nfull * TILE + lp; i < a.n; i += LP) {
+            const T x = a.x[i], d = a.d[i], w = a.w[i];
+#pragma unroll
+            for (int k = 0; k < CPT; k++) {
+                const T r = (mdl[k].eval(x) - d) * w;
+                tacc[k] = fma(r, r, tacc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CPT; k++) acc[k] += (double)tacc[k];
+    }
+
+#pragma unroll
+    for (int k = 0; k < CPT; k++) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o >= LC; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int64_t c = cbase + (int64_t)k * LC;
+        if (lp == 0 && c < a.nchains) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = v;
+    }
+}
+
+// Shape policy (pure function of nchains, n, dtype).
+struct Shape { int lc, cpt, nsplit; int64_t groups; };
+
+Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
+    Shape s;
+    s.lc = nchains >= 96 ? 32 : (nchains >= 12 ? 8 : 1);
+    s.cpt = 1;
+    const int tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
+    s.groups = ceil_div64(nchains, (int64_t)WARPS * s.lc * s.cpt);
+    const int64_t nfull = n / tile;
+    int64_t want = ceil_div64((int64_t)sms * 8, s.groups);     // ~8 CTAs per SM
+    int64_t ns = want < 1 ? 1 : want;
+    if (ns > nfull) ns = nfull;
+    if (ns > MC3B_MAX_SPLIT) ns = MC3B_MAX_SPLIT;
+    if (ns < 1) ns = 1;
+    s.nsplit = (int)ns;
+    return s;
+}
+
+template <class M, typename T>
+int launch_model_chisq(const Shape& sh, ChisqArgs<T> a, int nsplit, cudaStream_t st) {
+    dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
+    if (sh.lc == 32) k_model_chisq<M, T, 32, 1><<<grid, block, 0, st>>>(a);
+    else if (sh.lc == 8) k_model_chisq<M, T, 8, 1><<<grid, block, 0, st>>>(a);
+    else k_model_chisq<M, T, 1, 1><<<grid, block, 0, st>>>(a);
+    MC3B_CHECK_LAUNCH("k_model_chisq");
+    return MC3B_OK;
+}
+
+template <typename T>
+int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchains, int nmodel,
+                  const void* x, const void* d, const void* w, int64_t n, double* partial, int64_t ldpartial,
+                  int nsplit, int dtype, cudaStream_t st) {
+    ChisqArgs<T> a;
+    a.params = params; a.ldp = ldp; a.nchains = nchains;
+    a.x = (const T*)x; a.d = (const T*)d; a.w = (const T*)w; a.n = n; a.partial = partial; a.ldpartial = ldpartial;
+    a.use_tma = ((((uintptr_t)x | (uintptr_t)d | (uintptr_t)w) & 15) == 0) ? 1 : 0;
+    Shape sh = plan_shape(nchains, n, dtype, mc3b_sm_count());
+    MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
+    MC3B_DISPATCH_MODEL(T, model_id, nmodel, return (launch_model_chisq<M, T>(sh, a, nsplit, st)));
+    return MC3B_OK;
+}
+
+// ---- model values (best_model, func(params) shape probe) -------------------
+template <class M>
+__global__ void k_model_eval(const double* params, int64_t ldp, const double* x, int64_t n, double* out) {
+    M m;
+    m.load(params + (int64_t)blockIdx.y * ldp);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[(int64_t)blockIdx.y * n + i] = m.eval(x[i]);
+}
+
+// ---- sum of partials + priors ----------------------------------------------
+__global__ void k_chisq_finish(const double* partial, int64_t ldpartial, int nsplit, int64_t nchains, const double* params,
+                               int64_t ldp, int npars, const double* prior, const double* plo,
+                               const double* pup, double* chisq) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; s++) acc += partial[(int64_t)s * ldpartial + c];
+    if (prior != nullptr) {
+        double pr = 0.0;
+        for (int j = 0; j < npars; j++) {
+            const double lo = plo[j], up = pup[j];
+            if (lo > 0.0 && up > 0.0) {
+                const double off = params[c * ldp + j] - prior[j];
+                const double t = off / (off > 0.0 ? up : lo);
+                pr += t * t;
+            }
+        }
+        acc += pr;
+    }
+    chisq[c] = acc;
+}
+
+// ---- chi-squared of given models (user callables): HBM-bound ---------------
+// One CTA per chain row; 256 threads stride the row (coalesced 8-byte loads),
+// fixed-order reduction (lane tree, then warps in order).
+__global__ void __launch_bounds__(256) k_chisq_rows(const double* model, int64_t ldm, const double* data,
+                                                    const double* uncert, int64_t n, double* chisq) {
+    const double* m = model + (int64_t)blockIdx.x * ldm;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+        const double r = (m[i] - data[i]) / uncert[i];
+        acc = fma(r, r, acc);
+    }
+    __shared__ double ws[8];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; k++) t += ws[k];
+        chisq[blockIdx.x] = t;
+    }
+}
+
+__global__ void k_residuals(const double* model, const double* data, const double* uncert, int64_t n,
+                            const double* off, const double* low, const double* up, int64_t np, double* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (model[i] - data[i]) / uncert[i];
+    else if (i < n + np) {
+        const int64_t k = i - n;
+        out[i] = off[k] / (off[k] > 0.0 ? up[k] : low[k]);
+    }
+}
+
+}  // namespace
+
+extern "C" int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit) {
+    MC3B_CHECK_ARG(nchains > 0 && n > 0 && nsplit != nullptr, "bad plan arguments");
+    MC3B_CHECK_ARG(dtype == MC3B_F64 || dtype == MC3B_F32, "bad dtype %d", dtype);
+    int sms = mc3b_sm_count();
+    if (sms <= 0) sms = 148;        // planning without a device (CPU-side sizing)
+    *nsplit = plan_shape(nchains, n, dtype, sms).nsplit;
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,
+                                int nmodel, const void* x, const void* data, const void* invsig, int64_t n,
+                                double* partial, int64_t ldpartial, int nsplit, void* stream) {
+    MC3B_CHECK_ARG(params && x && data && invsig && partial, "null pointer");
+    MC3B_CHECK_ARG(ldpartial >= nchains, "ldpartial < nchains");
+    MC3B_CHECK_ARG(nchains > 0 && n > 0 && nmodel > 0 && nmodel <= ldp, "bad sizes");
+    MC3B_CHECK_ARG(mc3b_model_nparams(model_id, nmodel) == nmodel, "model %d does not take %d parameters",
+                   model_id, nmodel);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == MC3B_F64)
+        return model_chisq_t<double>(model_id, params, ldp, nchains, nmodel, x, data, invsig, n, partial, ldpartial,
+                                     nsplit, dtype, st);
+    if (dtype == MC3B_F32)
+        return model_chisq_t<float>(model_id, params, ldp, nchains, nmodel, x, data, invsig, n, partial, ldpartial,
+                                    nsplit, dtype, st);
+    mc3b_set_error("bad dtype %d", dtype);
+    return MC3B_ERR_ARG;
+}
+
+extern "C" int mc3b_model_eval(int model_id, const double* params, int64_t ldp, int64_t nchains, int nmodel,
+                               const double* x, int64_t n, double* out, void* stream) {
+    MC3B_CHECK_ARG(params && x && out && nchains > 0 && n > 0, "bad arguments");
+    MC3B_CHECK_ARG(mc3b_model_nparams(model_id, nmodel) == nmodel, "model %d does not take %d parameters",
+                   model_id, nmodel);
+    MC3B_CHECK_ARG(nchains <= 65535, "model_eval is for small batches (<= 65535 rows)");
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t bx = ceil_div64(n, 256);
+    if (bx > 1184) bx = 1184;
+    dim3 grid((unsigned)bx, (unsigned)nchains);
+    MC3B_DISPATCH_MODEL(double, model_id, nmodel, (k_model_eval<M><<<grid, 256, 0, st>>>(params, ldp, x, n, out)));
+    MC3B_CHECK_LAUNCH("k_model_eval");
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_chisq_finish(const double* partial, int64_t ldpartial, int nsplit, int64_t nchains, const double* params,
+                                 int64_t ldp, int npars, const double* prior, const double* priorlow,
+                                 const double* priorup, double* chisq, void* stream) {
+    MC3B_CHECK_ARG(partial && chisq && nsplit > 0 && nchains > 0, "bad arguments");
+    MC3B_CHECK_ARG(prior == nullptr || (params && priorlow && priorup), "priors need params, priorlow, priorup");
+    k_chisq_finish<<<(unsigned)ceil_div64(nchains, 128), 128, 0, (cudaStream_t)stream>>>(
+        partial, ldpartial, nsplit, nchains, params, ldp, npars, prior, priorlow, priorup, chisq);
+    MC3B_CHECK_LAUNCH("k_chisq_finish");
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_chisq_batch(const double* model, int64_t ldm, int64_t nchains, const double* data,
+                                const double* uncert, int64_t n, double* chisq, void* stream) {
+    MC3B_CHECK_ARG(model && data && uncert && chisq && nchains > 0 && n > 0 && ldm >= n, "bad arguments");
+    k_chisq_rows<<<(unsigned)nchains, 256, 0, (cudaStream_t)stream>>>(model, ldm, data, uncert, n, chisq);
+    MC3B_CHECK_LAUNCH("k_chisq_rows");
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_residuals(const double* model, const double* data, const double* uncert, int64_t n,
+                              const double* off, const double* low, const double* up, int64_t np, double* out,
+                              void* stream) {
+    MC3B_CHECK_ARG(model && data && uncert && out && n > 0, "bad arguments");
+    if (off == nullptr) np = 0;
+    k_residuals<<<(unsigned)ceil_div64(n + np, 256), 256, 0, (cudaStream_t)stream>>>(model, data, uncert, n, off,
+                                                                                      low, up, np, out);
+    MC3B_CHECK_LAUNCH("k_residuals");
+    return MC3B_OK;
+}

@@ -1,0 +1,65 @@
+// mc3_b200 -- error state, device queries, FMA-peak microbenchmark.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mc3b_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mc3b_sm_count() {
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { cudaGetLastError(); return -1; }
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+extern "C" int mc3b_version(void) { return MC3B_VERSION; }
+extern "C" const char* mc3b_last_error(void) { return g_err; }
+extern "C" int mc3b_device_sms(void) { return mc3b_sm_count(); }
+
+// Roofline denominator: 8 independent accumulators per thread, each a chain of
+// dependent FMAs; 256 threads x 8 CTAs per SM keeps the pipe full.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(int64_t iters, double* sink) {
+    T a[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = (T)(threadIdx.x + k) * (T)1e-3;
+    const T m = (T)0.999999, c = (T)1e-7;
+    for (int64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = fma(a[k], m, c);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == (T)123456.789) sink[0] = (double)s;     // never true; keeps the loop alive
+}
+}  // namespace
+
+extern "C" int mc3b_fma_peak(int dtype, int64_t iters, double* sink, double* flops, void* stream) {
+    MC3B_CHECK_ARG(sink && flops && iters > 0, "bad arguments");
+    int sms = mc3b_sm_count();
+    MC3B_CHECK_ARG(sms > 0, "no CUDA device");
+    const int ctas = sms * 8;
+    if (dtype == MC3B_F64) k_fma_peak<double><<<ctas, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else if (dtype == MC3B_F32) k_fma_peak<float><<<ctas, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+    else { mc3b_set_error("bad dtype %d", dtype); return MC3B_ERR_ARG; }
+    MC3B_CHECK_LAUNCH("k_fma_peak");
+    *flops = 2.0 * 8.0 * 256.0 * (double)ctas * (double)iters;
+    return MC3B_OK;
+}

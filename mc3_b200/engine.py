@@ -1,0 +1,491 @@
+"""Device-resident chain population: the B200 replacement of the reference's
+per-iteration loop (mc3/chain.py:158-299) and of the shared state that
+mc3/mcmc_driver.py:143-202 allocates.
+
+One `Population` = all chains of one device.  A generation is three kernel
+launches through the C ABI (include/mc3b200.h):
+
+    mc3b_propose      draws, jump, bounds, shared fill        chain.py:185-247
+    mc3b_model_chisq  built-in model + chi-squared, all chains  chain.py:249, 302-340
+    mc3b_metropolis   partial sums + priors, accept, write    chain.py:251-289
+
+advancing every chain in lock-step (SURVEY.md finding 6: within one generation
+all chains see the population / history as it was at the start of the
+generation).  The generation counter can live on the device so that the three
+launches are captured once in a CUDA graph and replayed.
+
+Replay mode (`replay`) consumes the reference's recorded random stream and
+walks the chains in the reference's sequential order, to retrace its
+accept/reject trajectory.
+
+HBM layout (all fp64 unless noted; row-major):
+    x, data, invsig [N]     (+ fp32 copies in dtype='f32')
+    X         [nchains, nfree]   current states          (reference `freepars`)
+    Z         [zlen, nfree]      history, reference row order: M0 initial rows,
+                                 then row M0 + k*nchains + c for thinned step k
+    log_post  [zlen], zchain [zlen] int32 (-1 = initial sample)
+    nextp     [nchains, npars]   proposed full vectors
+    partial   [nsplit, nchains]  per-split chi-squared partial sums
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models import BuiltinModel, TorchModel
+from .parallel import chain_slice, allgather_rows, gather_history, sum_owned
+
+_DT = {'f64': _lib.F64, 'f32': _lib.F32, np.float64: _lib.F64, np.float32: _lib.F32}
+
+
+class Population:
+    def __init__(self, data, uncert, func, params, indparams=(), indparams_dict=None,
+                 pstep=None, pmin=None, pmax=None, prior=None, priorlow=None,
+                 priorup=None, nchains=7, sampler='snooker', wlike=False,
+                 fgamma=1.0, fepsilon=0.0, hsize=10, thinning=1, nzchain=1,
+                 seed=0, dtype='f64', device=None, rank=0, world=1, group=None,
+                 reflect=False, M0=None):
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.Mc3bError('mc3_b200 needs a CUDA device (no CPU fallback)')
+        self.dev = torch.device('cuda', torch.cuda.current_device()) \
+            if device is None else torch.device(device)
+        self.rank, self.world, self.group = rank, world, group
+        self.func = func
+        self.indparams = list(indparams)
+        self.indparams_dict = dict(indparams_dict or {})
+        self.wlike = bool(wlike)
+        self.sampler = sampler
+        self.dtype = _DT[dtype]
+        f64 = dict(dtype=torch.float64, device=self.dev)
+
+        params = np.array(params, dtype=np.double)
+        self.npars = npars = params.size
+        self.params = params
+        self.pstep = np.asarray(pstep, dtype=np.double)
+        self.pmin = np.full(npars, -np.inf) if pmin is None else np.asarray(pmin, np.double)
+        self.pmax = np.full(npars, np.inf) if pmax is None else np.asarray(pmax, np.double)
+        if prior is None or priorlow is None or priorup is None:
+            prior = priorlow = priorup = np.zeros(npars)
+        self.prior = np.asarray(prior, np.double)
+        self.priorlow = np.asarray(priorlow, np.double)
+        self.priorup = np.asarray(priorup, np.double)
+        self.ifree = np.where(self.pstep > 0)[0]
+        self.ishare = np.where(self.pstep < 0)[0]
+        self.nfree = nfree = self.ifree.size
+        if npars > _lib.MAX_PARS:
+            raise ValueError(f'at most {_lib.MAX_PARS} parameters are supported')
+        self.nchains = int(nchains)
+        self.chain0, self.nlocal = chain_slice(self.nchains, rank, world)
+        self.hsize, self.thinning, self.nzchain = int(hsize), int(thinning), int(nzchain)
+        self.M0 = self.hsize*self.nchains if M0 is None else int(M0)
+        self.zlen = self.M0 + self.nzchain*self.nchains
+        self.seed = int(seed)
+
+        # ---- data ----
+        data = np.ascontiguousarray(data, dtype=np.double)
+        uncert = np.ascontiguousarray(uncert, dtype=np.double)
+        self.ndata = data.size
+        self.d_data = torch.from_numpy(data).to(self.dev)
+        self.d_uncert = torch.from_numpy(uncert).to(self.dev)
+        self.nfunc = npars - 3 if self.wlike else npars
+        if isinstance(func, BuiltinModel):
+            self.kind = 'builtin'
+            self.nmodel = func.nmodel(self.nfunc)
+            x = np.ascontiguousarray(self.indparams[0], dtype=np.double)
+            if x.shape != data.shape:
+                raise ValueError('built-in models need indparams=[x] with the '
+                                 'same shape as data')
+            self.d_x = torch.from_numpy(x).to(self.dev)
+            self.d_invsig = 1.0/self.d_uncert
+            if self.dtype == _lib.F32:
+                self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
+                                                (self.d_x, self.d_data, self.d_invsig))
+            else:
+                self.k_x, self.k_d, self.k_w = self.d_x, self.d_data, self.d_invsig
+        elif isinstance(func, TorchModel):
+            self.kind = 'torch'
+            self.t_indparams = [torch.as_tensor(a, device=self.dev)
+                                if isinstance(a, np.ndarray) else a
+                                for a in self.indparams]
+        else:
+            self.kind = 'numpy'
+
+        # ---- small vectors ----
+        self.d_ifree = torch.tensor(self.ifree, dtype=torch.int32, device=self.dev)
+        self.d_pstep = torch.tensor(self.pstep, **f64)
+        self.d_pmin = torch.tensor(self.pmin, **f64)
+        self.d_pmax = torch.tensor(self.pmax, **f64)
+        self.d_params0 = torch.tensor(params, **f64)
+        self.has_prior = bool(np.any((self.priorlow > 0) & (self.priorup > 0)))
+        self.d_prior = torch.tensor(self.prior, **f64)
+        self.d_priorlow = torch.tensor(self.priorlow, **f64)
+        self.d_priorup = torch.tensor(self.priorup, **f64)
+
+        # ---- population state ----
+        n = self.nchains
+        self.X = torch.zeros((n, nfree), **f64)
+        self.chisq_cur = torch.zeros(n, **f64)
+        self.Z = torch.zeros((self.zlen, nfree), **f64)
+        self.log_post = torch.zeros(self.zlen, **f64)
+        self.zchain = torch.full((self.zlen,), -1, dtype=torch.int32, device=self.dev)
+        self.nextp = torch.zeros((n, npars), **f64)
+        self.mrfactor = torch.ones(n, **f64)
+        self.u = torch.zeros(n, **f64)
+        self.inb = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.naccept = torch.zeros(n, dtype=torch.int32, device=self.dev)
+        self.outbounds = torch.zeros(nfree, dtype=torch.int32, device=self.dev)
+        self.best_chisq = torch.full((n,), float('inf'), **f64)
+        self.best_x = torch.zeros((n, nfree), **f64)
+        self.best_gen = torch.zeros(n, dtype=torch.int64, device=self.dev)
+        self.gen_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        self.gen = 0                      # generations completed
+        self.bestp0 = np.copy(params)     # best of the initial population
+        self.best_log_post0 = -np.inf
+
+        self._plans = {}
+        self._work = {}
+        self._graph = None
+        self.S = self._make_struct()
+        self.set_jump_scales(fgamma, fepsilon)
+        self.S.reflect = 1 if reflect else 0
+        self.launches = 0                 # kernels launched by this object
+
+    # ------------------------------------------------------------------
+    def _make_struct(self):
+        S = _lib.SamplerStruct()
+        S.nchains, S.chain0, S.nlocal = self.nchains, self.chain0, self.nlocal
+        S.npars, S.nfree = self.npars, self.nfree
+        S.sampler = _lib.SAMPLERS[self.sampler]
+        S.reflect = 0
+        S.ifree, S.pstep = self.d_ifree.data_ptr(), self.d_pstep.data_ptr()
+        S.pmin, S.pmax = self.d_pmin.data_ptr(), self.d_pmax.data_ptr()
+        S.params0 = self.d_params0.data_ptr()
+        if self.has_prior:
+            S.prior, S.priorlow = self.d_prior.data_ptr(), self.d_priorlow.data_ptr()
+            S.priorup = self.d_priorup.data_ptr()
+        S.gamma = 0.0
+        S.fepsilon = 0.0
+        S.seed = self.seed
+        S.X, S.chisq_cur = self.X.data_ptr(), self.chisq_cur.data_ptr()
+        S.Z, S.log_post, S.zchain = (self.Z.data_ptr(), self.log_post.data_ptr(),
+                                     self.zchain.data_ptr())
+        S.zlen, S.M0 = self.zlen, self.M0
+        S.nextp, S.mrfactor = self.nextp.data_ptr(), self.mrfactor.data_ptr()
+        S.u, S.inb = self.u.data_ptr(), self.inb.data_ptr()
+        S.naccept, S.outbounds = self.naccept.data_ptr(), self.outbounds.data_ptr()
+        S.best_chisq, S.best_x = self.best_chisq.data_ptr(), self.best_x.data_ptr()
+        S.best_gen = self.best_gen.data_ptr()
+        S.gen_dev, S.thinning = self.gen_dev.data_ptr(), self.thinning
+        return S
+
+    def set_jump_scales(self, fgamma, fepsilon):
+        self.S.gamma = float(fgamma)*2.38/np.sqrt(2*self.nfree)   # chain.py:175
+        self.S.fepsilon = float(fepsilon)
+
+    # ------------------------------------------------------------------
+    # chi-squared of a batch of full parameter vectors
+    # ------------------------------------------------------------------
+    def _plan(self, nb):
+        if nb not in self._plans:
+            ns = ctypes.c_int(0)
+            _lib.call('mc3b_model_chisq_plan', nb, self.ndata, self.dtype,
+                      ctypes.byref(ns))
+            self._plans[nb] = ns.value
+        return self._plans[nb]
+
+    def _workspace(self, key, shape, dtype=torch.float64):
+        t = self._work.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=self.dev)
+            self._work[key] = t
+        return t
+
+    def _model_rows(self, P):
+        """Model values [nb, N] on the device for non-built-in models."""
+        if self.kind == 'torch':
+            Pm = P[:, :self.nfunc]
+            m = self.func.fn(Pm, *self.t_indparams, **self.indparams_dict)
+            return m.to(torch.float64).contiguous()
+        Ph = P.cpu().numpy()
+        rows = np.empty((Ph.shape[0], self.ndata))
+        for i in range(Ph.shape[0]):     # the reference's per-chain host callable
+            rows[i] = self.func(Ph[i, :self.nfunc], *self.indparams,
+                                **self.indparams_dict)
+        return torch.from_numpy(rows).to(self.dev)
+
+    def data_chisq(self, P):
+        """(partial, ld, nsplit) holding the data chi-squared of rows of P."""
+        nb = P.shape[0]
+        st = _lib.stream_ptr()
+        if self.wlike:
+            out = self._workspace(('dwt', nb), (1, nb))
+            ws_bytes = _lib.load().mc3b_dwt_workspace(nb, self.ndata)
+            ws = self._workspace(('dwtws', nb), (max(ws_bytes, 8)//8,))
+            if self.kind == 'builtin':
+                _lib.call('mc3b_dwt_chisq', self.func.model_id, P.data_ptr(),
+                          P.stride(0), nb, self.npars, self.nmodel,
+                          self.d_x.data_ptr(), None, 0, self.d_data.data_ptr(),
+                          self.ndata, ws.data_ptr(), out.data_ptr(), st)
+            else:
+                m = self._model_rows(P)
+                _lib.call('mc3b_dwt_chisq', -1, P.data_ptr(), P.stride(0), nb,
+                          self.npars, 0, None, m.data_ptr(), m.stride(0),
+                          self.d_data.data_ptr(), self.ndata, ws.data_ptr(),
+                          out.data_ptr(), st)
+            self.launches += 2
+            return out, nb, 1
+        if self.kind == 'builtin':
+            ns = self._plan(nb)
+            part = self._workspace(('part', nb), (ns, nb))
+            _lib.call('mc3b_model_chisq', self.func.model_id, self.dtype,
+                      P.data_ptr(), P.stride(0), nb, self.nmodel,
+                      self.k_x.data_ptr(), self.k_d.data_ptr(),
+                      self.k_w.data_ptr(), self.ndata, part.data_ptr(), nb, ns, st)
+            self.launches += 1
+            return part, nb, ns
+        m = self._model_rows(P)
+        out = self._workspace(('rows', nb), (1, nb))
+        _lib.call('mc3b_chisq_batch', m.data_ptr(), m.stride(0), nb,
+                  self.d_data.data_ptr(), self.d_uncert.data_ptr(), self.ndata,
+                  out.data_ptr(), st)
+        self.launches += 1
+        return out, nb, 1
+
+    def chisq(self, P):
+        """chi-squared + prior terms of full parameter vectors P [nb, npars]."""
+        P = P.contiguous()
+        nb = P.shape[0]
+        part, ld, ns = self.data_chisq(P)
+        out = torch.empty(nb, dtype=torch.float64, device=self.dev)
+        pr = (self.d_prior.data_ptr(), self.d_priorlow.data_ptr(),
+              self.d_priorup.data_ptr()) if self.has_prior else (None, None, None)
+        _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, P.data_ptr(),
+                  P.stride(0), self.npars, *pr, out.data_ptr(), _lib.stream_ptr())
+        self.launches += 1
+        return out
+
+    # ------------------------------------------------------------------
+    # initial population   (mcmc_driver.py:229-278)
+    # ------------------------------------------------------------------
+    def init_population(self, kickoff='normal'):
+        kick = {'normal': 0, 'uniform': 1}[kickoff]
+        M0 = self.M0
+        got = 0
+        tried = 0
+        rnd = 0
+        rows, lps = [], []
+        while got < M0 and tried < 100*M0:
+            nt = int(min(max(M0 - got, 64)*1.25 + 64, 100*M0 - tried))
+            trial = torch.empty((nt, self.npars), dtype=torch.float64, device=self.dev)
+            ok = torch.empty(nt, dtype=torch.int32, device=self.dev)
+            _lib.call('mc3b_init_trials', ctypes.byref(self.S), kick, nt, rnd,
+                      trial.data_ptr(), ok.data_ptr(), _lib.stream_ptr())
+            self.launches += 1
+            lp = -0.5*self.chisq(trial)
+            good = (ok != 0) & torch.isfinite(lp)
+            idx = torch.nonzero(good).flatten()[:M0 - got]
+            rows.append(trial[idx])
+            lps.append(lp[idx])
+            got += idx.numel()
+            tried += nt
+            rnd += 1
+        if got < M0:
+            raise ValueError(
+                'Cannot populate an initial sample set of parameters, try '
+                'updating the parameters initial guess to avoid sampling '
+                'beyond the parameter boundaries or where the model returns '
+                'non-finite values.')
+        full = torch.cat(rows)
+        self.set_initial(full[:, self.d_ifree.long()], torch.cat(lps))
+
+    def set_initial(self, Z0, log_post0):
+        """Install M0 initial history rows and start every chain from row c
+        (chain.py:163-170: chain c starts at Z[c], chisq = -2 log_post[c])."""
+        Z0 = torch.as_tensor(Z0, dtype=torch.float64, device=self.dev)
+        lp0 = torch.as_tensor(log_post0, dtype=torch.float64, device=self.dev)
+        assert Z0.shape == (self.M0, self.nfree)
+        self.Z[:self.M0] = Z0
+        self.log_post[:self.M0] = lp0
+        self.X.copy_(self.Z[:self.nchains])
+        self.chisq_cur.copy_(-2.0*self.log_post[:self.nchains])
+        iz = int(torch.argmax(lp0))                  # mcmc_driver.py:273-275
+        self.best_log_post0 = float(lp0[iz])
+        self.bestp0 = np.copy(self.params)
+        self.bestp0[self.ifree] = Z0[iz].cpu().numpy()
+        for s in self.ishare:
+            self.bestp0[s] = self.bestp0[-int(self.pstep[s]) - 1]
+
+    # ------------------------------------------------------------------
+    # one lock-step generation
+    # ------------------------------------------------------------------
+    def _zrow0(self, gen):
+        if (gen + 1) % self.thinning:
+            return -1
+        return self.M0 + ((gen + 1)//self.thinning - 1)*self.nchains
+
+    def _generation(self, gen):
+        """gen >= 0: host-driven; gen < 0: device-driven (graph capture)."""
+        st = _lib.stream_ptr()
+        c0, c1 = self.chain0, self.chain0 + self.nlocal
+        zsize = self.M0 + (gen//self.thinning)*self.nchains if gen >= 0 else 0
+        _lib.call('mc3b_propose', ctypes.byref(self.S), gen, zsize, c0, c1, st)
+        part, ld, ns = self.data_chisq(self.nextp[c0:c1])
+        zrow0 = self._zrow0(gen) if gen >= 0 else -1
+        _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(), ld, ns,
+                  c0, gen, zrow0, c0, c1, st)
+        self.launches += 2
+        if self.world > 1:
+            self._exchange(gen)
+        if gen < 0:
+            _lib.call('mc3b_advance', ctypes.byref(self.S), st)
+            self.launches += 1
+
+    def _exchange(self, gen):
+        """Per-generation population exchange across devices:
+        demc needs every chain's current state, snooker the new history rows."""
+        if self.sampler == 'demc':
+            allgather_rows(self.X, self.chain0, self.nlocal, self.group)
+        elif self.sampler == 'snooker':
+            if gen < 0:
+                raise _lib.Mc3bError('multi-GPU snooker runs host-driven generations')
+            r0 = self._zrow0(gen)
+            if r0 >= 0:
+                allgather_rows(self.Z[r0:r0 + self.nchains], self.chain0,
+                               self.nlocal, self.group)
+
+    def run(self, ngen, use_graph=None):
+        """Advance `ngen` generations."""
+        if ngen <= 0:
+            return
+        if use_graph is None:
+            use_graph = self.kind == 'builtin' and not \
+                (self.world > 1 and self.sampler == 'snooker')
+        if not use_graph:
+            for g in range(self.gen, self.gen + ngen):
+                self._generation(g)
+            self.gen += ngen
+            self.gen_dev.fill_(self.gen)
+            return
+        if self._graph is None:
+            self.gen_dev.fill_(self.gen)
+            self._generation(self.gen)          # warm-up outside capture
+            self.gen += 1
+            self.gen_dev.fill_(self.gen)
+            ngen -= 1
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            before = self.launches
+            with torch.cuda.graph(g):
+                self._generation(-1)
+            self._graph_launches = self.launches - before
+            self.launches = before
+            self._graph = g
+        for _ in range(ngen):
+            self._graph.replay()
+        self.launches += ngen*self._graph_launches
+        self.gen += ngen
+
+    # ------------------------------------------------------------------
+    # replay of the reference's recorded stream (sequential chain order)
+    # ------------------------------------------------------------------
+    def replay(self, draws, ngen=None):
+        """draws: dict of arrays from oracle DrawLog.arrays() (normal, a, b, iz,
+        usj, gs, u, done).  Chains are stepped one at a time for demc/snooker
+        (chain j sees chains < j already moved, chain.py:190-289)."""
+        G = int(draws['ngen']) if ngen is None else int(ngen)
+        dv = {}
+        for k in ('normal', 'usj', 'gs', 'u'):
+            dv[k] = torch.as_tensor(np.ascontiguousarray(draws[k]),
+                                    dtype=torch.float64, device=self.dev)
+        for k in ('a', 'b', 'iz'):
+            dv[k] = torch.as_tensor(np.ascontiguousarray(draws[k]),
+                                    dtype=torch.int64, device=self.dev)
+        done = np.asarray(draws['done'])
+        st = _lib.stream_ptr()
+        n = self.nchains
+        D = _lib.DrawsStruct()
+        for g in range(G):
+            D.normal = dv['normal'][g].data_ptr()
+            for k in ('a', 'b', 'iz', 'usj', 'gs', 'u'):
+                setattr(D, k, dv[k][g].data_ptr())
+            nd = int(done[g].sum())               # chains that ran this generation
+            complete = nd == n
+            zrow0 = self._zrow0(self.gen) if complete else -1
+            if self.sampler == 'mrw':
+                groups = [(0, nd)]
+            else:
+                groups = [(c, c + 1) for c in range(nd)]
+            for c0, c1 in groups:
+                _lib.call('mc3b_propose_replay', ctypes.byref(self.S),
+                          ctypes.byref(D), c0, c1, st)
+                part, ld, ns = self.data_chisq(self.nextp[c0:c1])
+                _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(),
+                          ld, ns, c0, self.gen, zrow0, c0, c1, st)
+                self.launches += 2
+            self.gen += 1
+        self.gen_dev.fill_(self.gen)
+
+    # ------------------------------------------------------------------
+    # hub-side reads
+    # ------------------------------------------------------------------
+    def thinned_done(self):
+        return self.gen//self.thinning
+
+    def zsize(self):
+        return self.M0 + self.thinned_done()*self.nchains
+
+    def gather_history(self):
+        """Make Z / log_post / zchain complete on every device (no-op at world=1)."""
+        for t in (self.Z, self.log_post, self.zchain):
+            gather_history(t, self.M0, self.thinned_done(), self.nchains,
+                           self.rank, self.world, self.group)
+
+    def counters(self):
+        """Host copy of the counters (summed over devices)."""
+        nacc, oob = self.naccept, self.outbounds
+        bc, bx, bg = self.best_chisq, self.best_x, self.best_gen
+        if self.world > 1:
+            import torch.distributed as dist
+            lo, n = self.chain0, self.nlocal
+            nacc, bg, bx = (sum_owned(t, lo, n, self.group) for t in (nacc, bg, bx))
+            fin = torch.where(torch.isfinite(bc), bc, torch.zeros_like(bc))
+            isf = sum_owned(torch.isfinite(bc).to(torch.float64), lo, n, self.group)
+            bc = sum_owned(fin, lo, n, self.group)
+            bc = torch.where(isf > 0, bc, torch.full_like(bc, float('inf')))
+            oob = oob.clone()
+            dist.all_reduce(oob, group=self.group)
+        bc_h = bc.cpu().numpy()
+        bg_h = bg.cpu().numpy()
+        numaccept = int(nacc.sum()) + getattr(self, 'resumed_accept', 0)
+        # chain.py:268-274 -- first strictly lower chi-squared in (generation,
+        # chain) order wins; start from the best of the initial population.
+        best_chisq = -2.0*self.best_log_post0
+        bestp = np.copy(self.bestp0)
+        cand = np.where(bc_h < best_chisq)[0]
+        if cand.size:
+            m = bc_h[cand].min()
+            tie = cand[bc_h[cand] == m]
+            c = tie[np.lexsort((tie, bg_h[tie]))[0]]
+            best_chisq = float(bc_h[c])
+            bestp[self.ifree] = bx[c].cpu().numpy()
+            for s in self.ishare:
+                bestp[s] = bestp[-int(self.pstep[s]) - 1]
+        return dict(numaccept=numaccept, outbounds=oob.cpu().numpy().astype(int),
+                    bestp=bestp, best_log_post=-0.5*best_chisq)
+
+    def gelman_rubin(self, zburn):
+        """PSRF per free parameter over the thinned samples after burn-in."""
+        K = self.thinned_done()
+        niter = K - zburn
+        if niter < 1:
+            return np.zeros(self.nfree)
+        self.gather_history()
+        work = self._workspace('gr', (2, self.nchains, self.nfree))
+        psrf = torch.empty(self.nfree, dtype=torch.float64, device=self.dev)
+        _lib.call('mc3b_gelman_rubin', self.Z.data_ptr(), self.nfree, self.nchains,
+                  self.M0, None, 0, zburn, niter, work.data_ptr(), psrf.data_ptr(),
+                  _lib.stream_ptr())
+        self.launches += 2
+        return psrf.cpu().numpy()

@@ -1,0 +1,218 @@
+"""The MCMC hub: same call signature and output dictionary as the reference's
+mc3.mcmc_driver.mcmc (mc3/mcmc_driver.py:18-378), with the forked Chain
+processes, shared ctypes arrays and pipes replaced by one device-resident
+Population (engine.py) advanced in lock-step by CUDA kernels.
+
+What is kept from the reference, line for line in behaviour:
+  sizes          nzchain, niter, zlen, zburn, grnmin rule   mcmc_driver.py:116-198
+  initial set    hsize*nchains accepted draws, best of them  :229-278
+  reports        every 10%: progress, out-of-bounds, best, savefile, GR test,
+                 grbreak early stop                          :297-348
+  output         update_output keys                          stats.py:805-852
+What differs by design: chains advance together (Jacobi order) and random
+numbers come from per-chain Philox streams, so runs agree with the reference
+statistically, not draw for draw (use Population.replay for the latter).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import stats as ms
+from . import utils as mu
+from .engine import Population
+from .models import BuiltinModel, TorchModel
+
+
+def eval_model(pop, params, ret='model'):
+    """Chain.eval_model for one parameter vector (chain.py:302-340), on the GPU."""
+    P = torch.as_tensor(np.atleast_2d(np.asarray(params, float)), device=pop.dev)
+    chisq = float(pop.chisq(P)[0])
+    if ret == 'chisq':
+        return chisq
+    fpar = np.asarray(params, float)[:pop.nfunc]
+    if isinstance(pop.func, (BuiltinModel, TorchModel)):
+        model = pop.func(fpar, *pop.indparams, **pop.indparams_dict)
+    else:
+        model = pop.func(fpar, *pop.indparams, **pop.indparams_dict)
+    return (model, chisq) if ret == 'both' else model
+
+
+def calc_bestfit_statistics(bestp, pop):
+    """stats.py:855-873."""
+    ndata = pop.ndata
+    best_model, opt_chisq = eval_model(pop, bestp, 'both')
+    best_log_post = -0.5*opt_chisq
+    best_log_prior = ms.log_prior(bestp[pop.ifree], pop.prior, pop.priorlow,
+                                  pop.priorup, pop.pstep)
+    best_chisq = -2*(best_log_post - best_log_prior)
+    bic = best_chisq + pop.nfree*np.log(ndata)
+    red = best_chisq/(ndata - pop.nfree) if ndata > pop.nfree else np.nan
+    data = pop.d_data.cpu().numpy()
+    return best_chisq, red, bic, best_log_post, best_model, np.std(best_model - data)
+
+
+def update_output(output, pop, hsize, counters=None):
+    """stats.py:805-852 -- fill the output dict from the device state."""
+    pop.gather_history()
+    zburn = output['burnin']
+    n = pop.zsize()
+    Z = pop.Z[:n].cpu().numpy()
+    zchain = pop.zchain[:n].cpu().numpy().astype(int)
+    log_post = pop.log_post[:n].cpu().numpy()
+    c = counters or pop.counters()
+    zvalid = zchain >= 0
+    nsample = np.sum(zvalid)*pop.thinning
+    lpr = ms.log_prior(Z[zvalid], pop.prior, pop.priorlow, pop.priorup, pop.pstep) \
+        if np.any(zvalid) else np.zeros(0)
+    output['posterior'] = Z[zvalid]
+    output['zchain'] = zchain[zvalid]
+    output['chisq'] = -2.0*(log_post[zvalid] - lpr)
+    output['log_post'] = log_post[zvalid]
+    output['acceptance_rate'] = c['numaccept']*100.0/max(nsample, 1)
+    bestp = c['bestp']
+    best = calc_bestfit_statistics(bestp, pop)
+    output['bestp'] = bestp
+    (output['best_chisq'], output['red_chisq'], output['BIC'],
+     output['best_log_post'], output['best_model'],
+     output['stddev_residuals']) = best
+    if not pop.thinned_done() > zburn:
+        return None
+    posterior, _, zmask = mu.burn(Z=Z[zvalid], zchain=zchain[zvalid], burnin=zburn)
+    st = ms.calc_sample_statistics(posterior, bestp, pop.pstep)
+    output['zmask'] = zmask
+    (output['medianp'], output['meanp'], output['stdp'],
+     output['median_low_bounds'], output['median_high_bounds']) = st
+    return posterior
+
+
+def mcmc(data, uncert, func, params, indparams, indparams_dict,
+         pmin, pmax, pstep, prior, priorlow, priorup, nchains, ncpu, nsamples,
+         sampler, wlike, fit_output, grtest, grbreak, grnmin, burnin, thinning,
+         fgamma, fepsilon, hsize, kickoff, savefile, resume, log,
+         pnames, texnames, seed=None, dtype='f64', device=None, use_graph=None,
+         rank=0, world=1, group=None, reflect=False, return_population=False):
+    """Reference signature (mcmc_driver.py:18-26; `ncpu` is accepted and
+    ignored) plus keyword-only device options."""
+    pstep = np.asarray(pstep, float)
+    nfree = int(np.sum(pstep > 0))
+    ifree = np.where(pstep > 0)[0]
+    nchains, thinning, hsize = int(nchains), int(thinning), int(hsize)
+
+    M0 = pre_zsize = hsize*nchains
+    oldrun = None
+    if resume:
+        oldrun = np.load(savefile)
+        M0 = pre_zsize = oldrun['posterior'].shape[0]
+
+    nzchain = int(np.ceil(nsamples/nchains/thinning))      # mcmc_driver.py:129-134
+    niter = nzchain*thinning
+    burnin = int(burnin)
+    if not resume and niter < burnin:
+        log.error(
+            f"The number of burned-in samples ({burnin}) is greater than "
+            f"the number of iterations per chain ({niter})")
+    zburn = int(burnin/thinning)
+
+    if grnmin >= 1:                                          # :186-198
+        grnmin = int(grnmin/thinning)
+    elif grnmin > 0:
+        grnmin = int(grnmin*nchains*(nzchain - zburn))
+    elif grnmin < 0:
+        log.error(
+            "Invalid 'grnmin' argument (minimum number of samples to "
+            "stop the MCMC under GR convergence), must either be grnmin > 1"
+            "to set the minimum number of samples, or 0 < grnmin < 1"
+            "to set the fraction of samples required to evaluate.")
+    grnmin += int(M0 + zburn*nchains)
+
+    if seed is None:
+        seed = int(np.random.randint(0, 2**31 - 1))
+    pop = Population(
+        data, uncert, func, params, indparams, indparams_dict, pstep, pmin,
+        pmax, prior, priorlow, priorup, nchains=nchains, sampler=sampler,
+        wlike=wlike, fgamma=fgamma, fepsilon=fepsilon, hsize=hsize,
+        thinning=thinning, nzchain=nzchain, seed=seed, dtype=dtype,
+        device=device, rank=rank, world=world, group=group, reflect=reflect,
+        M0=M0)
+
+    if resume:
+        _resume(pop, oldrun)
+    else:
+        try:
+            pop.init_population(kickoff)
+        except ValueError as e:
+            log.error(str(e))
+        if fit_output is not None:                           # :276-278
+            pop.bestp0 = np.copy(fit_output['bestp'])
+            pop.best_log_post0 = float(fit_output['best_log_post'])
+
+    output = {'pnames': pnames, 'texnames': texnames, 'pstep': pstep,
+              'ifree': ifree, 'burnin': zburn}
+
+    if rank == 0:
+        print("Yippee Ki Yay Monte Carlo!")
+    log.msg(f"Start MCMC chains  ({time.ctime()})")
+    # Reports every tenth of the run, on whole thinned generations (:297-348).
+    step_k = max(1, int(np.ceil(nzchain/10)))
+    k_done = 0
+    while k_done < nzchain:
+        k_next = min(nzchain, k_done + step_k)
+        pop.run((k_next - k_done)*thinning, use_graph=use_graph)
+        k_done = k_next
+        c = pop.counters()
+        log.progressbar(k_done/nzchain)
+        log.msg(
+            f"Out-of-bound Trials:\n{c['outbounds']}\n"
+            f"Best Parameters: (chisq={-2*c['best_log_post']:.4f})\n"
+            f"{c['bestp'][ifree]}", width=80)
+        if savefile is not None and rank == 0:
+            update_output(output, pop, hsize, c)
+            np.savez(savefile, **output)
+        if grtest and k_done > zburn:
+            psrf = pop.gelman_rubin(zburn)
+            log.msg(f"Gelman-Rubin statistics for free parameters:\n{psrf}",
+                    width=80)
+            if np.all(psrf < 1.01):
+                log.msg("All parameters converged to within 1% of unity.")
+            if grbreak > 0.0 and np.all(psrf < grbreak) and pop.zsize() > grnmin:
+                log.msg(
+                    "\nAll parameters satisfy the GR convergence "
+                    f"threshold of {grbreak:g}, stopping the MCMC.")
+                break
+
+    posterior = update_output(output, pop, hsize)
+    Z = output['posterior']
+    nsample = len(Z)*thinning
+    nzsample = 0 if posterior is None else len(posterior)
+    fmt = len(str(nsample))
+    log.msg('\nMCMC Summary:\n-------------')
+    log.msg(
+        f"Number of evaluated samples:        {nsample:{fmt}d}\n"
+        f"Number of parallel chains:          {nchains:{fmt}d}\n"
+        f"Average iterations per chain:       {nsample//nchains:{fmt}d}\n"
+        f"Burned-in iterations per chain:     {burnin:{fmt}d}\n"
+        f"Thinning factor:                    {thinning:{fmt}d}\n"
+        f"MCMC sample size (thinned, burned): {nzsample:{fmt}d}\n"
+        f"Acceptance rate:   {output['acceptance_rate']:.2f}%\n", indent=2)
+    if return_population:
+        output['_population'] = pop
+    return output
+
+
+def _resume(pop, oldrun):
+    """mcmc_driver.py:178-184, 223-227 + chain.py:166-169: previous samples
+    become the initial history; every chain restarts from its last row."""
+    zold = np.asarray(oldrun['posterior'], float)
+    zc = np.asarray(oldrun['zchain']).astype(int)
+    lp = np.asarray(oldrun['log_post'], float)
+    M0 = zold.shape[0]
+    pop.Z[:M0] = torch.as_tensor(zold, device=pop.dev)
+    pop.log_post[:M0] = torch.as_tensor(lp, device=pop.dev)
+    pop.zchain[:M0] = torch.as_tensor(zc, dtype=torch.int32, device=pop.dev)
+    last = np.array([np.where(zc == c)[0][-1] for c in range(pop.nchains)])
+    pop.X.copy_(pop.Z[torch.as_tensor(last, device=pop.dev)])
+    pop.chisq_cur.copy_(-2.0*pop.log_post[torch.as_tensor(last, device=pop.dev)])
+    pop.bestp0 = np.array(oldrun['bestp'], float)
+    pop.best_log_post0 = float(oldrun['best_log_post'])
+    pop.resumed_accept = int(float(oldrun['acceptance_rate'])/100.0*M0)

@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing: chains are partitioned across the GPUs of one box
+(contiguous blocks, one process per GPU) and exchanged with NCCL through
+torch.distributed.  Replaces the reference's shared ctypes
+arrays + pipes (mc3/mcmc_driver.py:143-221, 302-307).
+
+What travels, per generation:
+  mrw      nothing (chains are independent)
+  demc     all-gather of the current states X [nchains, nfree]   (chain.py:231)
+  snooker  all-gather of the history rows written this generation (chain.py:197-217)
+and at report points the thinned history / counters.  Every function here works
+on plain tensors, so the same code runs under gloo on CPU in the tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def chain_slice(nchains, rank, world):
+    """(first chain, number of chains) owned by `rank`: contiguous blocks."""
+    if nchains % world != 0:
+        raise ValueError(f'nchains ({nchains}) must be a multiple of the '
+                         f'number of devices ({world})')
+    nlocal = nchains // world
+    return rank*nlocal, nlocal
+
+
+def allgather_rows(block, chain0, nlocal, group=None):
+    """In-place all-gather of `block` [nchains, w]: every rank contributes rows
+    [chain0, chain0+nlocal) and receives all the others."""
+    mine = block[chain0:chain0 + nlocal]
+    if dist.get_backend(group) == 'nccl':
+        dist.all_gather_into_tensor(block.view(-1), mine.reshape(-1), group=group)
+    else:                                   # gloo: no in-place flat gather
+        parts = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, mine.contiguous(), group=group)
+        block.copy_(torch.cat(parts).view_as(block))
+
+
+def gather_history(t, M0, K, nchains, rank, world, group=None):
+    """Complete the thinned history tensor t ([zlen] or [zlen, w]) on every rank.
+    Row M0 + k*nchains + c belongs to the owner of chain c; K thinned steps."""
+    if world == 1 or K == 0:
+        return
+    nlocal = nchains // world
+    w = 1 if t.dim() == 1 else t.shape[1]
+    v = t[M0:M0 + K*nchains].view(K, world, nlocal*w)
+    mine = v[:, rank].contiguous()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    v.copy_(torch.stack(parts, dim=1))
+
+
+def sum_owned(t, chain0, nlocal, group=None):
+    """All-reduce a per-chain tensor of which each rank only owns a slice."""
+    m = torch.zeros_like(t)
+    m[chain0:chain0 + nlocal] = t[chain0:chain0 + nlocal]
+    dist.all_reduce(m, group=group)
+    return m

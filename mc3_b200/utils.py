@@ -1,0 +1,103 @@
+"""Small host utilities behind the drop-in API: the logger whose error() is the
+reference's error convention (mc3/utils/log.py:219-240 -> raises ValueError
+with the message), burn-in masking (mc3/utils/utils.py:260-344) and default
+parameter names (utils.py:347-361)."""
+import sys
+import textwrap
+import time
+
+import numpy as np
+
+
+class Log:
+    """stdout (+ optional file) logger with the reference's verbosity levels:
+    verb < 0 errors only, >= 0 warnings, >= 1 head, >= 2 msg, >= 3 debug."""
+
+    def __init__(self, logname=None, verb=2, append=False, width=70):
+        self.logname = logname
+        self.file = open(logname, 'a' if append else 'w') if logname else None
+        self.verb, self.width, self.indent = verb, width, 0
+        self.warnings = []
+        self.sep = 70*':'
+
+    def write(self, text):
+        print(text)
+        sys.stdout.flush()
+        if self.file is not None and not self.file.closed:
+            self.file.write(text + '\n')
+            self.file.flush()
+
+    def wrap(self, message, indent=None, si=None, width=None):
+        indent = self.indent if indent is None else indent
+        si = self.indent if si is None else si
+        width = self.width if width is None else width
+        lines = [textwrap.fill(s, width=width, initial_indent=' '*indent,
+                               subsequent_indent=' '*si, break_long_words=False,
+                               break_on_hyphens=False)
+                 for s in message.splitlines()]
+        return '\n'.join(lines)
+
+    def _emit(self, level, message, **kw):
+        if self.verb >= level:
+            self.write(self.wrap(message, **kw))
+
+    def msg(self, message, verb=2, **kw):
+        self._emit(verb, message, **kw)
+
+    def head(self, message, **kw):
+        self._emit(1, message, **kw)
+
+    def debug(self, message, **kw):
+        self._emit(3, message, **kw)
+
+    def warning(self, message):
+        text = f'\n{self.sep}\n  Warning:\n{self.wrap(message, indent=4)}\n{self.sep}\n'
+        self.warnings.append(message)
+        if self.verb >= 0:
+            self.write(text)
+
+    def error(self, message, exception=ValueError):
+        text = f'\n{self.sep}\n  Error:\n{self.wrap(message, indent=4)}\n{self.sep}\n'
+        if self.file is not None and not self.file.closed:
+            self.file.write(text + '\n')
+            self.file.close()
+        raise exception(message)
+
+    def progressbar(self, frac):
+        if self.verb >= 2:
+            n = int(np.clip(10*frac, 0, 10))
+            bar = ':'*n + ' '*(10 - n)
+            self.write(f'\n[{bar}] {100*frac:5.1f}% completed  ({time.ctime()})')
+
+    def close(self):
+        if self.file is not None and not self.file.closed:
+            self.file.close()
+
+
+def default_parnames(npars):
+    return np.array([f'Param {i+1}' for i in range(npars)])
+
+
+def burn(Zdict=None, burnin=None, Z=None, zchain=None, sort=True):
+    """Drop the first `burnin` samples of every chain; returns (posterior,
+    zchain, zmask) with the reference's ordering rules (utils.py:322-344)."""
+    if Zdict is None and (Z is None or zchain is None or burnin is None):
+        raise ValueError(
+            'Need to input either Zdict or all three of burnin, Z, and zchain')
+    if Zdict is not None:
+        Z, zchain = Zdict['posterior'], Zdict['zchain']
+        if burnin is None:
+            burnin = Zdict['burnin']
+    zchain = np.asarray(zchain)
+    # rank of each sample within its own chain, vectorised over chains
+    order = np.argsort(zchain, kind='stable')
+    zs = zchain[order]
+    first = np.searchsorted(zs, zs, side='left')
+    rank = np.empty(zchain.size, dtype=np.int64)
+    rank[order] = np.arange(zchain.size) - first
+    mask = (zchain >= 0) & (rank >= burnin)
+    if sort:
+        zmask = order[mask[order]]
+    else:
+        zmask = np.where(mask)[0]
+    return Z[zmask], zchain[zmask], zmask

@@ -1,0 +1,353 @@
+"""GPU parity of the CUDA kernels, called through the C ABI, against the oracle
+(oracle/) and the reference's golden outputs (tests/golden/kernels.npz).
+fp64 tolerance 1e-10 relative, fp32 1e-5 (BASELINE.json north_star)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import kernels as ok
+from oracle import models as om
+from oracle import problems as pb
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+K = np.load(os.path.join(GOLD, 'kernels.npz'))
+R64, R32 = 1e-10, 1e-5
+
+
+@pytest.fixture(scope='module')
+def mc3():
+    import mc3_b200
+    return mc3_b200
+
+
+# ---- reference known answers through the drop-in wrappers -------------------
+def test_kat_chisq_residuals(mc3):
+    ms = mc3.stats
+    data = np.array([1.1, 1.2, 0.9, 1.0])
+    model, unc = np.ones(4), np.full(4, 0.1)
+    np.testing.assert_allclose(ms.chisq(model, data, unc), 6.0, rtol=1e-13)
+    args = (np.array([2.5, 5.5]), np.array([2.0, 5.0]), np.array([0.0, 1.0]),
+            np.array([0.0, 1.0]))
+    np.testing.assert_allclose(ms.chisq(model, data, unc, *args), 6.25, rtol=1e-13)
+    np.testing.assert_allclose(ms.residuals(model, data, unc),
+                               [-1.0, -2.0, 1.0, 0.0], atol=1e-13)
+    np.testing.assert_allclose(ms.residuals(model, data, unc, *args),
+                               [-1.0, -2.0, 1.0, 0.0, 0.5], atol=1e-13)
+
+
+def test_kat_dwt(mc3):
+    ms = mc3.stats
+    data = np.array([2.0, 0.0, 3.0, -2.0, -1.0, 2.0, 2.0, 0.0])
+    params = np.array([1.0, 0.1, 0.1])
+    np.testing.assert_allclose(ms.dwt_chisq(np.ones(8), data, params),
+                               1693.22308882)
+    c = ms.dwt_chisq(np.ones(8), data, params, np.array([1.0, 0.2, 0.3]),
+                     np.array([0.0, 0.0, 0.1]), np.array([0.0, 0.0, 0.1]))
+    np.testing.assert_allclose(c, 1697.2230888243134, rtol=1e-12)
+    with pytest.raises(ValueError, match='at least three parameters'):
+        ms.dwt_chisq(np.ones(8), data, params[:2])
+    with pytest.raises(ValueError, match='2\\*\\*k'):
+        ms.dwt_chisq(np.ones(7), data[:7], params)
+    e4 = np.zeros(32)
+    e4[4] = 1.0
+    from tests.test_oracle import DAUB4_FWD, DAUB4_INV
+    inv = ms.dwt_daub4(e4, True)
+    np.testing.assert_allclose(inv, DAUB4_INV, atol=1e-10)
+    np.testing.assert_allclose(ms.dwt_daub4(e4), DAUB4_FWD, atol=1e-10)
+    np.testing.assert_allclose(ms.dwt_daub4(inv), e4, atol=1e-8)
+
+
+def test_kat_bin_array(mc3):
+    ms = mc3.stats
+    data = np.array([0, 1, 2, 3, 3, 3, 3, 3, 4])
+    unc = np.array([3, 1, 1, 1, 2, 3, 2, 2, 4])
+    np.testing.assert_allclose(ms.bin_array(data, 3), [1.0, 3.0, 10/3])
+    bd, bs = ms.bin_array(data, 3, unc)
+    np.testing.assert_allclose(bd, [1.42105263, 3.0, 3.11111111])
+    np.testing.assert_allclose(bs, [0.68824720, 0.85714286, 1.33333333])
+
+
+def test_kat_time_avg(mc3):
+    from tests.test_oracle import RED_RMS, RED_RMSHI
+    white, red = pb.teststats_series()
+    rms, lo, hi, err, bsz = mc3.stats.time_avg(red, len(red)/10, 5)
+    np.testing.assert_almost_equal(rms, RED_RMS)
+    np.testing.assert_almost_equal(hi, RED_RMSHI)
+    np.testing.assert_almost_equal(bsz, 1 + 5*np.arange(20))
+    assert len(mc3.stats.time_avg(red)[0]) == 500
+    assert len(mc3.stats.time_avg(list(red), 500, 2)[0]) == 250
+
+
+# ---- golden outputs of the reference's C extensions -------------------------
+def test_golden_chisq(mc3):
+    ms = mc3.stats
+    c = pb.chisq_case()
+    np.testing.assert_allclose(ms.chisq(c['model'], c['data'], c['uncert']),
+                               K['chisq_noprior'], rtol=R64)
+    args = (c['params'], c['priors'], c['priorlow'], c['priorup'])
+    np.testing.assert_allclose(ms.chisq(c['model'], c['data'], c['uncert'], *args),
+                               K['chisq_prior'], rtol=R64)
+    np.testing.assert_allclose(ms.residuals(c['model'], c['data'], c['uncert'], *args),
+                               K['residuals_prior'], rtol=R64)
+
+
+@pytest.mark.parametrize('n', [8, 1024, 16384])
+def test_golden_dwt_chisq(mc3, n):
+    d = pb.dwt_case(n)
+    ms = mc3.stats
+    np.testing.assert_allclose(ms.dwt_chisq(d['model'], d['data'], d['params']),
+                               K[f'dwt_noprior_{n}'], rtol=R64)
+    np.testing.assert_allclose(
+        ms.dwt_chisq(d['model'], d['data'], d['params'], d['priors'],
+                     d['priorlow'], d['priorup']), K[f'dwt_prior_{n}'], rtol=R64)
+
+
+def test_golden_daub4(mc3):
+    rs = np.random.RandomState(3)
+    v1000, v4096 = rs.normal(0, 1, 1000), rs.normal(0, 1, 4096)
+    for v, tag in ((v1000, '1000'), (v4096, '4096')):
+        np.testing.assert_allclose(mc3.stats.dwt_daub4(v), K['daub4_fwd_' + tag],
+                                   rtol=R64, atol=1e-12)
+        np.testing.assert_allclose(mc3.stats.dwt_daub4(v, True),
+                                   K['daub4_inv_' + tag], rtol=R64, atol=1e-12)
+
+
+@pytest.mark.parametrize('key,args', [
+    ('tavg_red', ('red', 100, 5)), ('tavg_white', ('white', 100, 5)),
+    ('tavg_red_default', ('red', None, 1)), ('tavg_2000', (2000, 1000, 1)),
+    ('tavg_50k', (50000, 300, 7)), ('tavg_50k_big', (50000, 25000, 997))])
+def test_golden_time_avg(mc3, key, args):
+    src, maxbins, binstep = args
+    if src in ('red', 'white'):
+        white, red = pb.teststats_series()
+        data = red if src == 'red' else white
+    else:
+        data = pb.series_case(src, {2000: 5, 50000: 8}[src])
+    out = np.array(mc3.stats.time_avg(data, maxbins, binstep))
+    np.testing.assert_allclose(out, K[key], rtol=R64)
+
+
+@pytest.mark.parametrize('bs', [100, 7, 4099])
+def test_golden_bin_array(mc3, bs):
+    d, u = pb.binarray_case()
+    np.testing.assert_allclose(mc3.stats.bin_array(d, bs), K[f'bin_unw_{bs}'], rtol=R64)
+    np.testing.assert_allclose(np.array(mc3.stats.bin_array(d, bs, u)),
+                               K[f'bin_w_{bs}'], rtol=R64)
+
+
+def test_golden_gelman(mc3):
+    Z, zc, burn = pb.gelman_case()
+    np.testing.assert_allclose(mc3.stats.gelman_rubin(Z, zc, burn), K['gelman'],
+                               rtol=R64)
+
+
+# ---- fused model + chi-squared kernel vs the oracle --------------------------
+def _model_problem(name, n, seed):
+    rs = np.random.RandomState(seed)
+    if name == 'sinusoid':
+        x = np.linspace(0, 10, n)
+        p0 = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+        sc = np.array([0.05, 0.02, 0.1, 0.1, 0.01])
+    elif name == 'gaussian':
+        x = np.linspace(-5, 5, n)
+        p0 = np.array([2.0, 0.3, 1.2, 0.5])
+        sc = np.array([0.1, 0.1, 0.05, 0.05])
+    elif name == 'box':
+        x = np.linspace(-0.5, 0.5, n)
+        p0 = np.array([0.01, 0.0, 0.1, 1.0])
+        sc = np.array([1e-3, 1e-2, 1e-2, 1e-3])
+    else:
+        deg = int(name[4:])
+        x = np.linspace(-1, 1, n)
+        p0 = rs.normal(0, 1, deg)
+        sc = np.full(deg, 0.05)
+        name = 'polynomial'
+    uncert = rs.uniform(0.5, 1.5, n)*0.1
+    data = om.MODELS[name](p0, x) + rs.normal(0, 1, n)*uncert
+    return name, x, data, uncert, p0, sc
+
+
+def _run_model_chisq(mc3, name, P, x, data, uncert, dtype, prior=None):
+    from mc3_b200 import _lib
+    dev = torch.device('cuda')
+    model = mc3.models.BUILTIN[name]
+    nb, npars = P.shape
+    dP = torch.from_numpy(P).to(dev)
+    tdt = torch.float64 if dtype == 'f64' else torch.float32
+    dx = torch.from_numpy(x).to(dev).to(tdt)
+    dd = torch.from_numpy(data).to(dev).to(tdt)
+    dw = (1.0/torch.from_numpy(uncert).to(dev)).to(tdt)
+    code = _lib.F64 if dtype == 'f64' else _lib.F32
+    ns = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_plan', nb, x.size, code, ctypes.byref(ns))
+    part = torch.empty((ns.value, nb), dtype=torch.float64, device=dev)
+    _lib.call('mc3b_model_chisq', model.model_id, code, dP.data_ptr(), npars, nb,
+              model.nmodel(npars), dx.data_ptr(), dd.data_ptr(), dw.data_ptr(),
+              x.size, part.data_ptr(), nb, ns.value, _lib.stream_ptr())
+    out = torch.empty(nb, dtype=torch.float64, device=dev)
+    if prior is None:
+        _lib.call('mc3b_chisq_finish', part.data_ptr(), nb, ns.value, nb, None, 0,
+                  0, None, None, None, out.data_ptr(), _lib.stream_ptr())
+    else:
+        pr = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in prior]
+        _lib.call('mc3b_chisq_finish', part.data_ptr(), nb, ns.value, nb,
+                  dP.data_ptr(), npars, npars, pr[0].data_ptr(), pr[1].data_ptr(),
+                  pr[2].data_ptr(), out.data_ptr(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize('name', ['sinusoid', 'gaussian', 'box', 'poly1', 'poly3',
+                                  'poly5', 'poly8'])
+@pytest.mark.parametrize('nchains,n', [(1, 37), (7, 1000), (40, 4097), (300, 2560),
+                                       (1000, 5000)])
+def test_model_chisq_fp64(mc3, name, nchains, n):
+    mname, x, data, uncert, p0, sc = _model_problem(name, n, 100 + nchains)
+    rs = np.random.RandomState(nchains)
+    P = p0 + rs.normal(0, 1, (nchains, p0.size))*sc
+    got = _run_model_chisq(mc3, mname, P, x, data, uncert, 'f64')
+    want = np.array([ok.chisq(om.MODELS[mname](p, x), data, uncert) for p in P])
+    np.testing.assert_allclose(got, want, rtol=R64)
+
+
+@pytest.mark.parametrize('name', ['sinusoid', 'gaussian', 'box', 'poly3'])
+def test_model_chisq_fp32(mc3, name):
+    mname, x, data, uncert, p0, sc = _model_problem(name, 20000, 7)
+    P = p0 + np.random.RandomState(3).normal(0, 1, (256, p0.size))*sc
+    got = _run_model_chisq(mc3, mname, P, x, data, uncert, 'f32')
+    want = np.array([ok.chisq(om.MODELS[mname](p, x), data, uncert) for p in P])
+    np.testing.assert_allclose(got, want, rtol=R32)
+
+
+def test_model_chisq_priors_and_unaligned(mc3):
+    """Two-sided Gaussian priors (stats.h:102-106) and inputs that are not
+    16-byte aligned (the kernel must leave the TMA path)."""
+    mname, x, data, uncert, p0, sc = _model_problem('sinusoid', 3001, 5)
+    P = p0 + np.random.RandomState(1).normal(0, 1, (33, 5))*sc
+    prior = (np.array([0.0, 2.5, 0.0, 5.0, 0.0]), np.array([0.0, 0.1, 0.0, 0.2, 0.0]),
+             np.array([0.0, 0.1, 0.0, 0.4, 0.0]))
+    got = _run_model_chisq(mc3, mname, P, x, data, uncert, 'f64', prior)
+    want = np.array([ok.chisq(om.sinusoid(p, x), data, uncert, p, *prior) for p in P])
+    np.testing.assert_allclose(got, want, rtol=R64)
+    # odd element offset -> 8-byte aligned only
+    got2 = _run_model_chisq(mc3, mname, P, x[1:], data[1:], uncert[1:], 'f64')
+    want2 = np.array([ok.chisq(om.sinusoid(p, x[1:]), data[1:], uncert[1:]) for p in P])
+    np.testing.assert_allclose(got2, want2, rtol=R64)
+
+
+def test_model_chisq_full_size_properties(mc3):
+    """BASELINE config-2 size (4096 chains x 1e5 points): identical chains give
+    identical results, permuting chains permutes results (bit-exact), and a
+    sample of chains matches the oracle."""
+    mname, x, data, uncert, p0, sc = _model_problem('sinusoid', 100000, 11)
+    rs = np.random.RandomState(2)
+    P = p0 + rs.normal(0, 1, (4096, 5))*sc
+    P[100] = P[7]
+    got = _run_model_chisq(mc3, mname, P, x, data, uncert, 'f64')
+    assert got[100] == got[7]
+    perm = rs.permutation(4096)
+    got_p = _run_model_chisq(mc3, mname, P[perm], x, data, uncert, 'f64')
+    assert np.array_equal(got_p, got[perm])
+    pick = rs.choice(4096, 16, replace=False)
+    want = np.array([ok.chisq(om.sinusoid(p, x), data, uncert) for p in P[pick]])
+    np.testing.assert_allclose(got[pick], want, rtol=R64)
+    # run-to-run determinism
+    assert np.array_equal(got, _run_model_chisq(mc3, mname, P, x, data, uncert, 'f64'))
+
+
+def test_chisq_batch_and_nonfinite(mc3):
+    rs = np.random.RandomState(4)
+    n = 5003
+    data, unc = rs.normal(0, 1, n), rs.uniform(0.5, 2, n)
+    models = rs.normal(0, 1, (9, n))
+    models[3, 17] = np.inf
+    got = mc3.stats.chisq(models, data, unc)
+    want = np.array([ok.chisq(m, data, unc) for m in models])
+    assert np.isinf(got[3]) and np.isinf(want[3])
+    keep = np.arange(9) != 3
+    np.testing.assert_allclose(got[keep], want[keep], rtol=R64)
+
+
+def test_builtin_models_evaluate_on_gpu(mc3):
+    x = np.linspace(0, 10, 1001)
+    for name, p in (('sinusoid', [1.0, 2.5, 0.3, 5.0, -0.2]), ('gaussian', [2.0, 5.0, 1.2, 0.5]),
+                    ('box', [0.01, 5.0, 1.0, 1.0]), ('polynomial', [3.0, -2.4, 0.5])):
+        got = mc3.models.BUILTIN[name](np.array(p), x)
+        np.testing.assert_allclose(got, om.MODELS[name](np.array(p), x), rtol=1e-13,
+                                   atol=1e-13)
+
+
+# ---- wavelet likelihood with built-in model, batched ------------------------
+@pytest.mark.parametrize('n', [64, 512, 2048, 65536])
+def test_dwt_chisq_builtin_batched(mc3, n):
+    from mc3_b200 import _lib
+    dev = torch.device('cuda')
+    rs = np.random.RandomState(n)
+    x = np.linspace(-0.5, 0.5, n)
+    ptrue = np.array([0.01, 0.0, 0.1, 1.0])
+    data = om.box(ptrue, x) + rs.normal(0, 1e-3, n)
+    nb = 13
+    P = np.tile(np.array([0.01, 0.0, 0.1, 1.0, 1.0, 5e-3, 1e-3]), (nb, 1))
+    P[:, :4] += rs.normal(0, 1, (nb, 4))*np.array([1e-3, 1e-2, 1e-2, 1e-4])
+    P[:, 5:] *= rs.uniform(0.5, 2.0, (nb, 2))
+    dP, dx, dd = (torch.from_numpy(a).to(dev) for a in (P, x, data))
+    lib = _lib.load()
+    ws = torch.empty(max(lib.mc3b_dwt_workspace(nb, n), 8)//8, dtype=torch.float64,
+                     device=dev)
+    out = torch.empty(nb, dtype=torch.float64, device=dev)
+    _lib.call('mc3b_dwt_chisq', mc3.models.box.model_id, dP.data_ptr(), 7, nb, 7, 4,
+              dx.data_ptr(), None, 0, dd.data_ptr(), n, ws.data_ptr(),
+              out.data_ptr(), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    want = np.array([ok.dwt_chisq(om.box(p[:4], x), data, p) for p in P])
+    np.testing.assert_allclose(out.cpu().numpy(), want, rtol=R64)
+    # same through the model-rows entry (user callables)
+    rows = np.array([om.box(p[:4], x) for p in P])
+    got2 = mc3.stats.dwt_chisq(rows, data, P)
+    np.testing.assert_allclose(got2, want, rtol=R64)
+
+
+def test_daub4_roundtrip_large(mc3):
+    v = np.random.RandomState(8).normal(0, 1, 1 << 18)
+    f = mc3.stats.dwt_daub4(v)
+    np.testing.assert_allclose(f, ok.dwt_daub4(v), rtol=R64, atol=1e-12)
+    np.testing.assert_allclose(mc3.stats.dwt_daub4(f, True), v, atol=1e-10)
+    # Parseval: the D4 transform is orthogonal
+    np.testing.assert_allclose(np.sum(f*f), np.sum(v*v), rtol=1e-12)
+
+
+# ---- time series at scale: size-independent properties -----------------------
+def test_bin_array_large_properties(mc3):
+    n = 10_000_019
+    rs = np.random.RandomState(6)
+    d = rs.normal(1.0, 1.0, n)
+    b = mc3.stats.bin_array(d, 100)
+    assert b.size == n//100
+    np.testing.assert_allclose(b, d[:n//100*100].reshape(-1, 100).mean(axis=1), rtol=1e-12)
+    u = np.abs(rs.normal(0, 1, n)) + 0.5
+    bw, bs = mc3.stats.bin_array(d, 1000, u)
+    w = 1.0/u[:n//1000*1000].reshape(-1, 1000)**2
+    np.testing.assert_allclose(bs, np.sqrt(1.0/w.sum(axis=1)), rtol=1e-12)
+    np.testing.assert_allclose(
+        bw, (d[:n//1000*1000].reshape(-1, 1000)*w).sum(axis=1)/w.sum(axis=1), rtol=1e-11)
+
+
+def test_time_avg_large_matches_direct(mc3):
+    n = 2_000_003
+    d = pb.series_case(n, 21)
+    rms, lo, hi, err, bsz = mc3.stats.time_avg(d, 1000, 37)
+    for i in (0, 1, 13, len(rms) - 1):
+        b = int(bsz[i])
+        M = n//b
+        means = d[:M*b].reshape(M, b).mean(axis=1)
+        np.testing.assert_allclose(rms[i], np.sqrt(np.mean(means**2)), rtol=R64)
+        np.testing.assert_allclose(err[i], np.std(d)*np.sqrt(M/(b*(M - 1.0))), rtol=R64)
+        np.testing.assert_allclose(lo[i], rms[i]/np.sqrt(2.0*M), rtol=R64)
+    small = ok.time_avg(d[:200000], 1000, 37)
+    got = mc3.stats.time_avg(d[:200000], 1000, 37)
+    np.testing.assert_allclose(np.array(got), np.array(small), rtol=R64)

@@ -203,3 +203,29 @@ def test_golden_mcmc(case, sampler):
     np.testing.assert_allclose(b['bestp'], fx['ref_bestp'], rtol=1e-13)
     assert b['numaccept'] == int(fx['numaccept'])
     assert np.array_equal(b['outbounds'], fx['outbounds'])
+
+
+def test_fixture_decisions_are_not_marginal():
+    """Replay parity is meaningful only if no Metropolis decision of the
+    fixtures sits within rounding of its threshold: the relative gap between
+    exp(0.5 (chisq - chisq*)) and the uniform draw stays far above the 1e-10
+    band in which the CUDA chi-squared may differ from the reference's."""
+    worst = np.inf
+    for case in pb.MCMC_CASES:
+        for sampler in pb.SAMPLERS:
+            fx = np.load(os.path.join(GOLD, f'mcmc_{case}_{sampler}.npz'))
+            cur = -2.0*fx['log_post0'][:fx['draw_u'].shape[1]].copy()
+            G = int(fx['draw_ngen'])
+            for g in range(G):
+                for j in range(cur.size):
+                    if not fx['draw_done'][g, j] or not fx['draw_inb'][g, j]:
+                        continue
+                    prop, u = fx['draw_chisq'][g, j], fx['draw_u'][g, j]
+                    plain = sampler != 'snooker' or not fx['draw_usj'][g, j] < 0.1
+                    if plain and np.isfinite(prop):
+                        ratio = np.exp(0.5*(cur[j] - prop))
+                        assert (ratio > u) == bool(fx['draw_acc'][g, j])
+                        worst = min(worst, abs(ratio - u)/max(ratio, u))
+                    if fx['draw_acc'][g, j]:
+                        cur[j] = prop
+    assert worst > 1e-7, worst
