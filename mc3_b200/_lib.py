@@ -119,6 +119,12 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def ld(t):
+    """Row stride (in elements) of a 2-D row-major tensor; a single-row tensor
+    may carry a meaningless stride, so fall back to its width."""
+    return t.stride(0) if t.shape[0] > 1 else max(int(t.stride(0)), int(t.shape[1]))
+
+
 def stream_ptr():
     import torch
     return torch.cuda.current_stream().cuda_stream

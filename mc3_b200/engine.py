@@ -225,13 +225,13 @@ class Population:
             ws = self._workspace(('dwtws', nb), (max(ws_bytes, 8)//8,))
             if self.kind == 'builtin':
                 _lib.call('mc3b_dwt_chisq', self.func.model_id, P.data_ptr(),
-                          P.stride(0), nb, self.npars, self.nmodel,
+                          _lib.ld(P), nb, self.npars, self.nmodel,
                           self.d_x.data_ptr(), None, 0, self.d_data.data_ptr(),
                           self.ndata, ws.data_ptr(), out.data_ptr(), st)
             else:
                 m = self._model_rows(P)
-                _lib.call('mc3b_dwt_chisq', -1, P.data_ptr(), P.stride(0), nb,
-                          self.npars, 0, None, m.data_ptr(), m.stride(0),
+                _lib.call('mc3b_dwt_chisq', -1, P.data_ptr(), _lib.ld(P), nb,
+                          self.npars, 0, None, m.data_ptr(), _lib.ld(m),
                           self.d_data.data_ptr(), self.ndata, ws.data_ptr(),
                           out.data_ptr(), st)
             self.launches += 2
@@ -240,14 +240,14 @@ class Population:
             ns = self._plan(nb)
             part = self._workspace(('part', nb), (ns, nb))
             _lib.call('mc3b_model_chisq', self.func.model_id, self.dtype,
-                      P.data_ptr(), P.stride(0), nb, self.nmodel,
+                      P.data_ptr(), _lib.ld(P), nb, self.nmodel,
                       self.k_x.data_ptr(), self.k_d.data_ptr(),
                       self.k_w.data_ptr(), self.ndata, part.data_ptr(), nb, ns, st)
             self.launches += 1
             return part, nb, ns
         m = self._model_rows(P)
         out = self._workspace(('rows', nb), (1, nb))
-        _lib.call('mc3b_chisq_batch', m.data_ptr(), m.stride(0), nb,
+        _lib.call('mc3b_chisq_batch', m.data_ptr(), _lib.ld(m), nb,
                   self.d_data.data_ptr(), self.d_uncert.data_ptr(), self.ndata,
                   out.data_ptr(), st)
         self.launches += 1
@@ -262,7 +262,7 @@ class Population:
         pr = (self.d_prior.data_ptr(), self.d_priorlow.data_ptr(),
               self.d_priorup.data_ptr()) if self.has_prior else (None, None, None)
         _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, P.data_ptr(),
-                  P.stride(0), self.npars, *pr, out.data_ptr(), _lib.stream_ptr())
+                  _lib.ld(P), self.npars, *pr, out.data_ptr(), _lib.stream_ptr())
         self.launches += 1
         return out
 

@@ -76,6 +76,8 @@ class TorchModel:
         import torch
         p = torch.as_tensor(np.atleast_2d(np.asarray(params, dtype=np.double)),
                             device='cuda')
+        args = [torch.as_tensor(a, device='cuda') if isinstance(a, np.ndarray) else a
+                for a in args]
         out = self.fn(p, *args, **kwargs).detach().cpu().numpy()
         return out[0] if np.ndim(params) == 1 else out
 

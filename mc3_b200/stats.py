@@ -54,7 +54,7 @@ def _finish(part, nb, params, priors, priorlow, priorup):
             P = P.expand(nb, -1).contiguous()
         pr, lo, up = _up(priors), _up(priorlow), _up(priorup)
         _lib.call('mc3b_chisq_finish', part.data_ptr(), nb, 1, nb, P.data_ptr(),
-                  P.stride(0), P.shape[1], pr.data_ptr(), lo.data_ptr(),
+                  _lib.ld(P), P.shape[1], pr.data_ptr(), lo.data_ptr(),
                   up.data_ptr(), out.data_ptr(), st)
     return out
 
@@ -67,7 +67,7 @@ def chisq(model, data, uncert, params=None, priors=None, priorlow=None,
     d, u = _up(data), _up(uncert)
     nb, n = m.shape
     part = torch.empty(nb, dtype=torch.float64, device=m.device)
-    _lib.call('mc3b_chisq_batch', m.data_ptr(), m.stride(0), nb, d.data_ptr(),
+    _lib.call('mc3b_chisq_batch', m.data_ptr(), _lib.ld(m), nb, d.data_ptr(),
               u.data_ptr(), n, part.data_ptr(), _lib.stream_ptr())
     out = _finish(part, nb, params, priors, priorlow, priorup).cpu().numpy()
     return float(out[0]) if np.ndim(model) == 1 else out
@@ -112,8 +112,8 @@ def dwt_chisq(model, data, params, priors=None, priorlow=None, priorup=None):
     ws = torch.empty(max(lib.mc3b_dwt_workspace(nb, n), 8)//8,
                      dtype=torch.float64, device=m.device)
     part = torch.empty(nb, dtype=torch.float64, device=m.device)
-    _lib.call('mc3b_dwt_chisq', -1, P.data_ptr(), P.stride(0), nb, P.shape[1], 0,
-              None, m.data_ptr(), m.stride(0), d.data_ptr(), n, ws.data_ptr(),
+    _lib.call('mc3b_dwt_chisq', -1, P.data_ptr(), _lib.ld(P), nb, P.shape[1], 0,
+              None, m.data_ptr(), _lib.ld(m), d.data_ptr(), n, ws.data_ptr(),
               part.data_ptr(), _lib.stream_ptr())
     out = _finish(part, nb, params if priors is not None else None, priors,
                   priorlow, priorup).cpu().numpy()

@@ -55,7 +55,7 @@ def test_kat_dwt(mc3):
         ms.dwt_chisq(np.ones(7), data[:7], params)
     e4 = np.zeros(32)
     e4[4] = 1.0
-    from tests.test_oracle import DAUB4_FWD, DAUB4_INV
+    DAUB4_FWD, DAUB4_INV = pb.KAT_DAUB4_FWD, pb.KAT_DAUB4_INV
     inv = ms.dwt_daub4(e4, True)
     np.testing.assert_allclose(inv, DAUB4_INV, atol=1e-10)
     np.testing.assert_allclose(ms.dwt_daub4(e4), DAUB4_FWD, atol=1e-10)
@@ -73,7 +73,7 @@ def test_kat_bin_array(mc3):
 
 
 def test_kat_time_avg(mc3):
-    from tests.test_oracle import RED_RMS, RED_RMSHI
+    RED_RMS, RED_RMSHI = pb.KAT_RED_RMS, pb.KAT_RED_RMSHI
     white, red = pb.teststats_series()
     rms, lo, hi, err, bsz = mc3.stats.time_avg(red, len(red)/10, 5)
     np.testing.assert_almost_equal(rms, RED_RMS)

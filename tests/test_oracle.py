@@ -47,16 +47,7 @@ def test_kat_dwt_chisq():                              # test_stats.py:155-180
         ok.dwt_chisq(np.ones(8), data, params[:2])
 
 
-DAUB4_INV = np.array([
-    -0.0301851821, -0.0522822690, -0.0662912607, -0.0824674511, -0.0905555462,
-    -0.1008108399, -0.1132333322, -0.1250751254, 0.1325825215, 0.3180280110,
-    0.4312613433, 0.5638438647, 0.1412513157, -0.1325825215, -0.2576576469,
-    -0.4225925490, -0.1671021007, -0.0242642855, 0.0059208966, 0.0662912607,
-    0.0140089918, -0.0080880952] + [0.0]*10)
-DAUB4_FWD = np.array([
-    0.1625300592, 0.0874699408, -0.0463140877, 0.2795672632, -0.0905555462,
-    0.0, 0.0140089918, 0.1412513157, 0.3537658774, -0.0625, 0.0, 0.0, 0.0,
-    0.0, 0.0, -0.1082531755, 0.0, 0.8365163037, -0.1294095226] + [0.0]*13)
+DAUB4_INV, DAUB4_FWD = pb.KAT_DAUB4_INV, pb.KAT_DAUB4_FWD
 
 
 def test_kat_daub4():                                  # test_stats.py:70-86, 280-302
@@ -77,14 +68,7 @@ def test_kat_bin_array():                              # test_stats.py:96-112
     np.testing.assert_allclose(bs, [0.68824720, 0.85714286, 1.33333333])
 
 
-RED_RMS = [5.20512494, 2.36785563, 1.72466452, 1.49355819, 1.52934937,
-           1.35774105, 1.11881588, 1.13753563, 1.16566184, 1.03510878,
-           1.11692786, 0.95551055, 1.04041202, 0.86876758, 0.93962365,
-           0.95093077, 0.86283389, 0.89332354, 0.95500342, 0.82927083]
-RED_RMSHI = [0.11639013, 0.12995296, 0.1285489, 0.13412548, 0.15774034,
-             0.15574358, 0.1611256, 0.18169027, 0.20020244, 0.19264249,
-             0.22147211, 0.20384028, 0.23076986, 0.2007309, 0.22759927,
-             0.24306181, 0.23335404, 0.25645724, 0.29446565, 0.26262799]
+RED_RMS, RED_RMSHI = pb.KAT_RED_RMS, pb.KAT_RED_RMSHI
 
 
 def test_kat_time_avg():                               # test_stats.py:11-68, 306-343
