@@ -16,6 +16,7 @@
 //           point lanes, one partial per (split, chain): deterministic.
 //
 // Bound: FP64 (or FP32) pipe -- nchains*F flops per 24 bytes of data.
+#include <stdlib.h>
 #include "models.cuh"
 
 namespace {
@@ -157,7 +158,8 @@ struct Shape { int lc, cpt, nsplit; int64_t groups; };
 Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     Shape s;
     s.lc = nchains >= 96 ? 32 : (nchains >= 12 ? 8 : 1);
-    s.cpt = 1;
+    s.cpt = (s.lc == 32 && nchains >= 2048) ? 2 : 1;       // two chains per lane: tile reads amortised
+    if (const char* e = getenv("MC3B_CPT")) s.cpt = (s.lc == 32 && atoi(e) == 2) ? 2 : 1;
     const int tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
     s.groups = ceil_div64(nchains, (int64_t)WARPS * s.lc * s.cpt);
     const int64_t nfull = n / tile;
@@ -173,7 +175,8 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
 template <class M, typename T>
 int launch_model_chisq(const Shape& sh, ChisqArgs<T> a, int nsplit, cudaStream_t st) {
     dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
-    if (sh.lc == 32) k_model_chisq<M, T, 32, 1><<<grid, block, 0, st>>>(a);
+    if (sh.lc == 32 && sh.cpt == 2) k_model_chisq<M, T, 32, 2><<<grid, block, 0, st>>>(a);
+    else if (sh.lc == 32) k_model_chisq<M, T, 32, 1><<<grid, block, 0, st>>>(a);
     else if (sh.lc == 8) k_model_chisq<M, T, 8, 1><<<grid, block, 0, st>>>(a);
     else k_model_chisq<M, T, 1, 1><<<grid, block, 0, st>>>(a);
     MC3B_CHECK_LAUNCH("k_model_chisq");

@@ -351,3 +351,24 @@ def test_time_avg_large_matches_direct(mc3):
     small = ok.time_avg(d[:200000], 1000, 37)
     got = mc3.stats.time_avg(d[:200000], 1000, 37)
     np.testing.assert_allclose(np.array(got), np.array(small), rtol=R64)
+
+
+def test_fast_sin_accuracy(mc3):
+    """The kernel's branch-free fp64 sine (models.cuh fast_sin) against numpy:
+    sinusoid with p = [1, 2 pi, 0, 0, 0] is y = sin(x)."""
+    rs = np.random.RandomState(0)
+    p = np.array([1.0, 2.0*np.pi, 0.0, 0.0, 0.0])
+    xs = np.concatenate([
+        np.linspace(-50, 50, 200001), rs.uniform(-1e4, 1e4, 200000),
+        rs.uniform(-1e6, 1e6, 100000), np.pi*np.arange(-2000, 2000)/2.0,
+        np.array([0.0, 1e-300, -1e-300, 1e-8, 0.5, 1.5707963267948966, 3.141592653589793]),
+        rs.uniform(9e8, 1.1e9, 1000), rs.uniform(1e12, 1e15, 1000)])
+    got = mc3.models.sinusoid(p, xs)
+    want = np.sin(xs)
+    small = np.abs(xs) <= 1e6
+    assert np.max(np.abs(got - want)[small]) < 6e-16
+    assert np.max(np.abs(got - want)) < 2e-15          # library path beyond 1e9
+    assert got[xs == 0.0][0] == 0.0
+    tiny = np.abs(xs) == 1e-300
+    assert np.array_equal(got[tiny], xs[tiny])
+    assert np.isnan(mc3.models.sinusoid(p, np.array([np.inf, np.nan, 1.0, 2.0])))[:2].all()
