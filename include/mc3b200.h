@@ -189,6 +189,17 @@ int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial,
 int mc3b_init_trials(const mc3b_sampler_t* s, int kickoff, int64_t ntrials,
                      int64_t round, double* trial, int32_t* ok, void* stream);
 
+/* log_prior of nrows history rows Z [nrows, nfree] (mc3/stats/stats.py:367-392):
+ * lpr = -0.5 sum_j t_j^2, t_j = (z_j - prior)/priorlow|priorup for Gaussian priors,
+ * 2 log z_j where priorlow < 0, else 0 (prior* are [npars], ifree maps columns);
+ * and/or chisq = -2 (log_post - lpr) as update_output builds it (stats.py:822).
+ * lpr or chisq may be NULL. */
+int mc3b_log_prior(const double* Z, int64_t nrows, int nfree,
+                   const int32_t* ifree, const double* prior,
+                   const double* priorlow, const double* priorup,
+                   const double* log_post, double* lpr, double* chisq,
+                   void* stream);
+
 /* Gelman-Rubin PSRF per free parameter (gelman.py:36-92) over samples
  * k = burnin .. burnin+niter-1 of every chain; sample k of chain c is history
  * row  rows[c*ldr + k]  when rows != NULL, else  M0 + k*nchains + c  (the
@@ -254,6 +265,13 @@ int mc3b_binarray(const double* data, int64_t n, int64_t binsize,
  * Time it with events to get the FP64 / FP32 pipe peak. */
 int mc3b_fma_peak(int dtype, int64_t iters, double* sink, double* flops /*[host]*/,
                   void* stream);
+
+/* Same, with the operand kinds and parallelism of the model kernel (fp64):
+ * variant 1 = 8 chains/thread with constant-bank operands, 2 = 4 chains/thread
+ * at 6 CTAs of 128 threads per SM, 3 = 2 chains, 4 = 1 chain at 8 CTAs of 128.
+ * Used to read the FP64 dependent-issue latency off the device. */
+int mc3b_fma_peak_variant(int variant, int64_t iters, double* sink,
+                          double* flops /*[host]*/, void* stream);
 
 #ifdef __cplusplus
 }

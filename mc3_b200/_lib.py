@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'libmc3b200.so')
+LIBPATH = os.environ.get('MC3B_LIBPATH') or os.path.join(HERE, 'libmc3b200.so')
 
 OK, ERR_ARG, ERR_CUDA = 0, 1, 2
 F64, F32 = 0, 1
@@ -70,6 +70,8 @@ _SIGS = {
     'mc3b_advance': (c_int, [ctypes.POINTER(SamplerStruct), c_vp]),
     'mc3b_init_trials': (c_int, [ctypes.POINTER(SamplerStruct), c_int, c_i64, c_i64,
                                  c_vp, c_vp, c_vp]),
+    'mc3b_log_prior': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                               c_vp, c_vp]),
     'mc3b_gelman_rubin': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp]),
     'mc3b_dwt_workspace': (c_i64, [c_i64, c_i64]),
@@ -81,6 +83,7 @@ _SIGS = {
                             c_vp, c_vp, c_vp]),
     'mc3b_binarray': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     'mc3b_fma_peak': (c_int, [c_int, c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
+    'mc3b_fma_peak_variant': (c_int, [c_int, c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int WARPS = 4;
 constexpr int STAGES = 3;
+constexpr int RESIDENT = 6;     // CTAs per SM the register budget is tuned for (ILP over occupancy)
 template <typename T> struct tilecfg { static constexpr int TILE = 256; };
 template <> struct tilecfg<float> { static constexpr int TILE = 512; };
 
@@ -37,7 +38,7 @@ template <typename T> struct ChisqArgs {
 };
 
 template <class M, typename T, int LC, int CPT>
-__global__ void __launch_bounds__(WARPS * 32) k_model_chisq(ChisqArgs<T> a) {
+__global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<T> a) {
     constexpr int TILE = tilecfg<T>::TILE;
     constexpr int LP = 32 / LC;
     __shared__ __align__(128) T sx[STAGES][TILE];
@@ -84,16 +85,41 @@ __global__ void __launch_bounds__(WARPS * 32) k_model_chisq(ChisqArgs<T> a) {
         for (int64_t it = 0; it < nt; it++) {
             const int s = (int)(it % STAGES);
             mbar_wait(&bar[s], (uint32_t)((it / STAGES) & 1));
-            T tacc[CPT];
+            constexpr int U = 4;                // points in flight per lane
+            static_assert(TILE % (U * LP) == 0, "tile must hold whole groups");
+            T tacc[CPT], uacc[CPT][U];          // one accumulator per point slot: no serial tail
 #pragma unroll
-            for (int k = 0; k < CPT; k++) tacc[k] = (T)0;
-#pragma unroll 4
-            for (int i = lp; i < TILE; i += LP) {
-                const T x = sx[s][i], d = sd[s][i], w = sw[s][i];
+            for (int k = 0; k < CPT; k++) {
+#pragma unroll
+                for (int u = 0; u < U; u++) uacc[k][u] = (T)0;
+            }
+            for (int i = lp; i < TILE; i += U * LP) {
+                T x[U], y[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) x[u] = sx[s][i + u * LP];
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
-                    const T r = (mdl[k].eval(x) - d) * w;
-                    tacc[k] = fma(r, r, tacc[k]);
+                    eval_points<M, T, U>(mdl[k], x, y, 0);
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const T r = (y[u] - sd[s][i + u * LP]) * sw[s][i + u * LP];
+                        uacc[k][u] = fma(r, r, uacc[k][u]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPT; k++) tacc[k] = (uacc[k][0] + uacc[k][1]) + (uacc[k][2] + uacc[k][3]);
+            if (M::GUARD) {                     // extreme model arguments: redo the tile safely
+#pragma unroll
+                for (int k = 0; k < CPT; k++) {
+                    if (mdl[k].flagged()) {
+                        mdl[k].clear();
+                        tacc[k] = (T)0;
+                        for (int i = lp; i < TILE; i += LP) {
+                            const T r = (mdl[k].eval_safe(sx[s][i]) - sd[s][i]) * sw[s][i];
+                            tacc[k] = fma(r, r, tacc[k]);
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -116,7 +142,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_model_chisq(ChisqArgs<T> a) {
                 const T x = sx[0][i], d = sd[0][i], w = sw[0][i];
 #pragma unroll
                 for (int k = 0; k < CPT; k++) {
-                    const T r = (mdl[k].eval(x) - d) * w;
+                    const T r = (mdl[k].eval_safe(x) - d) * w;
                     tacc[k] = fma(r, r, tacc[k]);
                 }
             }
@@ -134,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_model_chisq(ChisqArgs<T> a) {
             const T x = a.x[i], d = a.d[i], w = a.w[i];
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
-                const T r = (mdl[k].eval(x) - d) * w;
+                const T r = (mdl[k].eval_safe(x) - d) * w;
                 tacc[k] = fma(r, r, tacc[k]);
             }
         }
@@ -158,12 +184,16 @@ struct Shape { int lc, cpt, nsplit; int64_t groups; };
 Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     Shape s;
     s.lc = nchains >= 96 ? 32 : (nchains >= 12 ? 8 : 1);
-    s.cpt = (s.lc == 32 && nchains >= 2048) ? 2 : 1;       // two chains per lane: tile reads amortised
+    s.cpt = 1;      // two chains per lane (MC3B_CPT=2) measured slower on B200: registers > tile-read savings
     if (const char* e = getenv("MC3B_CPT")) s.cpt = (s.lc == 32 && atoi(e) == 2) ? 2 : 1;
     const int tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
     s.groups = ceil_div64(nchains, (int64_t)WARPS * s.lc * s.cpt);
     const int64_t nfull = n / tile;
-    int64_t want = ceil_div64((int64_t)sms * 8, s.groups);     // ~8 CTAs per SM
+    int waves = 2;
+    if (const char* e = getenv("MC3B_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 1;
+    // whole waves of RESIDENT CTAs per SM (round to nearest: a few CTAs over one
+    // wave cost a whole extra wave, so round down unless clearly closer to the next)
+    int64_t want = ((int64_t)sms * RESIDENT * waves) / s.groups;
     int64_t ns = want < 1 ? 1 : want;
     if (ns > nfull) ns = nfull;
     if (ns > MC3B_MAX_SPLIT) ns = MC3B_MAX_SPLIT;
@@ -203,7 +233,7 @@ __global__ void k_model_eval(const double* params, int64_t ldp, const double* x,
     M m;
     m.load(params + (int64_t)blockIdx.y * ldp);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        out[(int64_t)blockIdx.y * n + i] = m.eval(x[i]);
+        out[(int64_t)blockIdx.y * n + i] = m.eval_safe(x[i]);
 }
 
 // ---- sum of partials + priors ----------------------------------------------

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_pass(PassArgs a) {
                 sd[i] = a.data[g];
             }
             __syncthreads();
-            for (int i = lane; i < len0; i += 32) buf0[i] = sd[i] - mdl.eval(sx[i]);
+            for (int i = lane; i < len0; i += 32) buf0[i] = sd[i] - mdl.eval_safe(sx[i]);
         } else if (SRC == SRC_GIVEN) {
             const double* m = a.rows + c * a.ldr;
             for (int i = lane; i < len0; i += 32) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(CHL * 32) k_dwt_last(LastArgs a) {
     if (SRC == SRC_MODEL) {
         M mdl;
         mdl.load(a.params + c * a.ldp);
-        for (int i = lane; i < a.n0; i += 32) in[i] = a.data[i] - mdl.eval(a.x[i]);
+        for (int i = lane; i < a.n0; i += 32) in[i] = a.data[i] - mdl.eval_safe(a.x[i]);
     } else if (SRC == SRC_GIVEN) {
         const double* m = a.rows + c * a.ldr;
         for (int i = lane; i < a.n0; i += 32) in[i] = a.data[i] - m[i];

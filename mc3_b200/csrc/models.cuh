@@ -23,26 +23,33 @@ __device__ __constant__ double kSinC[12] = {
     -1.2246467991473532e-16,     // -pi (low part)
     2.7314447669863995e-15, -7.643970296798572e-13, 1.6058977312464087e-10, -2.5052107616996182e-08,
     2.7557319219163234e-06, -0.00019841269841254974, 0.008333333333333316, -0.16666666666666666, 0.0};
+#define MC3B_SIN_MAGIC 6755399441055744.0               // 1.5 * 2^52
 
-__device__ __forceinline__ double fast_sin(double a) {
-    const double MAGIC = 6755399441055744.0;               // 1.5 * 2^52
-    const double t = fma(a, kSinC[0], MAGIC);               // low word = rint(a/pi)
-    const double q = t - MAGIC;
+// sin(a), no branches; `magic` holds MC3B_SIN_MAGIC in a register (so the FMA
+// below can take 1/pi from a uniform register).  Low word of t = rint(a/pi).
+__device__ __forceinline__ double fast_sin_core(double a, double magic) {
+    const double t = fma(a, kSinC[0], magic);
+    const double q = t - magic;
     double r = fma(q, kSinC[1], a);
     r = fma(q, kSinC[2], r);
     const double s = r * r;
-    double p = kSinC[3];
-    p = fma(p, s, kSinC[4]);
+    double p = fma(s, kSinC[3], kSinC[4]);
     p = fma(p, s, kSinC[5]);
     p = fma(p, s, kSinC[6]);
     p = fma(p, s, kSinC[7]);
     p = fma(p, s, kSinC[8]);
     p = fma(p, s, kSinC[9]);
     p = fma(p, s, kSinC[10]);
-    double v = fma(r * s, p, r);
-    v = __hiloint2double(__double2hiint(v) ^ (__double2loint(t) << 31), __double2loint(v));
-    if ((__double2hiint(a) & 0x7fffffff) >= 0x41cdcd65) v = sin(a);   // |a| >= 1e9, inf, nan
-    return v;
+    const double v = fma(r * s, p, r);
+    return __hiloint2double(__double2hiint(v) ^ (__double2loint(t) << 31), __double2loint(v));
+}
+// The fast path is valid for |a| < 1e9 (finite); callers check with this.
+__device__ __forceinline__ int sin_arg_key(double a) { return __double2hiint(a) & 0x7fffffff; }
+#define MC3B_SIN_KEY_LIMIT 0x41cdcd65
+
+__device__ __forceinline__ double fast_sin(double a) {
+    if (sin_arg_key(a) >= MC3B_SIN_KEY_LIMIT) return sin(a);   // |a| >= 1e9, inf, nan
+    return fast_sin_core(a, MC3B_SIN_MAGIC);
 }
 
 template <typename T> struct mathx;
@@ -56,7 +63,17 @@ template <> struct mathx<float> {
 };
 
 // y = sum_k p[k] x^k, NP coefficients (Horner).  get_started's quad() is NP=3.
+// Model interface used by the kernels:
+//   load(p)      once per chain per launch
+//   eval(x)      per point, branch-free; may be invalid for extreme arguments,
+//                in which case flagged() turns true
+//   flagged()    eval() met an argument outside its valid range since clear()
+//   eval_safe(x) always valid (slow path); clear() resets the flag
 template <typename T, int NP> struct PolyModel {
+    static constexpr bool GUARD = false;
+    __device__ __forceinline__ bool flagged() const { return false; }
+    __device__ __forceinline__ void clear() {}
+    __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
     T c[NP];
     __device__ __forceinline__ void load(const double* p) {
 #pragma unroll
@@ -72,6 +89,9 @@ template <typename T, int NP> struct PolyModel {
 
 // y = p0 sin(2 pi x / p1 + p2) + p3 + p4 x        (BASELINE config 2)
 template <typename T> struct SineModel {
+    static constexpr bool GUARD = false;
+    __device__ __forceinline__ bool flagged() const { return false; }
+    __device__ __forceinline__ void clear() {}
     T a, k, ph, c, s;
     __device__ __forceinline__ void load(const double* p) {
         a = (T)p[0]; k = (T)(6.283185307179586476925287 / p[1]); ph = (T)p[2];
@@ -80,10 +100,82 @@ template <typename T> struct SineModel {
     __device__ __forceinline__ T eval(T x) const {
         return fma(a, mathx<T>::sin_(fma(x, k, ph)), fma(s, x, c));
     }
+    __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
+};
+// fp64: branch-free sine inside the point loop (so the unrolled points
+// interleave); the largest |argument| seen is tracked with two integer ops and
+// checked once per tile by the kernel, which then redoes the tile with eval_safe.
+template <> struct SineModel<double> {
+    static constexpr bool GUARD = true;
+    double a, k, ph, c, s, magic;
+    int keymax;
+#ifdef MC3B_SIN_REGCONST
+    double K[11];
+#define KS(i) K[i]
+#else
+#define KS(i) kSinC[i]
+#endif
+    __device__ __forceinline__ void load(const double* p) {
+        a = p[0]; k = 6.283185307179586476925287 / p[1]; ph = p[2]; c = p[3]; s = p[4];
+        magic = MC3B_SIN_MAGIC;
+        asm volatile("" : "+d"(magic));          // keep it in a register
+#ifdef MC3B_SIN_REGCONST
+#pragma unroll
+        for (int i = 0; i < 11; i++) { K[i] = kSinC[i]; asm volatile("" : "+d"(K[i])); }
+#endif
+        keymax = 0;
+    }
+    __device__ __forceinline__ double eval(double x) {
+        const double arg = fma(x, k, ph);
+        keymax = max(keymax, sin_arg_key(arg));
+        return fma(a, fast_sin_core(arg, magic), fma(s, x, c));
+    }
+    template <int U> __device__ __forceinline__ void evalN(const double (&x)[U], double (&y)[U]) {
+        double arg[U], t[U], q[U], r[U], s2[U], p[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) arg[u] = fma(x[u], k, ph);
+#pragma unroll
+        for (int u = 0; u < U; u++) t[u] = fma(arg[u], KS(0), magic);
+#pragma unroll
+        for (int u = 0; u < U; u++) keymax = max(keymax, sin_arg_key(arg[u]));
+#pragma unroll
+        for (int u = 0; u < U; u++) q[u] = t[u] - magic;
+#pragma unroll
+        for (int u = 0; u < U; u++) r[u] = fma(q[u], KS(1), arg[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) r[u] = fma(q[u], KS(2), r[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) s2[u] = r[u] * r[u];
+#pragma unroll
+        for (int u = 0; u < U; u++) p[u] = fma(s2[u], KS(3), KS(4));
+#pragma unroll
+        for (int cidx = 5; cidx <= 10; cidx++) {
+#pragma unroll
+            for (int u = 0; u < U; u++) p[u] = fma(p[u], s2[u], KS(cidx));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) s2[u] = r[u] * s2[u];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double v = fma(s2[u], p[u], r[u]);
+            r[u] = __hiloint2double(__double2hiint(v) ^ (__double2loint(t[u]) << 31), __double2loint(v));
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) y[u] = fma(a, r[u], fma(s, x[u], c));
+    }
+    __device__ __forceinline__ bool flagged() const { return keymax >= MC3B_SIN_KEY_LIMIT; }
+    __device__ __forceinline__ void clear() { keymax = 0; }
+    __device__ __forceinline__ double eval_safe(double x) const {
+        return fma(a, sin(fma(x, k, ph)), fma(s, x, c));
+    }
 };
 
 // y = p0 exp(-0.5 ((x - p1)/p2)^2) + p3           (Gaussian line)
 template <typename T> struct GaussModel {
+    static constexpr bool GUARD = false;
+    __device__ __forceinline__ bool flagged() const { return false; }
+    __device__ __forceinline__ void clear() {}
+    __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
     T a, mu, is, c;
     __device__ __forceinline__ void load(const double* p) {
         a = (T)p[0]; mu = (T)p[1]; is = (T)(1.0 / p[2]); c = (T)p[3];
@@ -96,12 +188,29 @@ template <typename T> struct GaussModel {
 
 // y = p3 - p0 [ |x - p1| < p2/2 ]                 (transit-like box, config 3)
 template <typename T> struct BoxModel {
+    static constexpr bool GUARD = false;
+    __device__ __forceinline__ bool flagged() const { return false; }
+    __device__ __forceinline__ void clear() {}
+    __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
     T lo, base, t0, h;
     __device__ __forceinline__ void load(const double* p) {
         base = (T)p[3]; lo = (T)(p[3] - p[0]); t0 = (T)p[1]; h = (T)(0.5 * p[2]);
     }
     __device__ __forceinline__ T eval(T x) const { return (fabs(x - t0) < h) ? lo : base; }
 };
+
+// y[u] = model(x[u]) for U points at once.  Models may provide their own evalN
+// (stage-by-stage over the U points, so that in-order issue sees U independent
+// dependency chains); the default just loops.
+template <class M, typename T, int U>
+__device__ __forceinline__ auto eval_points(M& m, const T (&x)[U], T (&y)[U], int) -> decltype(m.evalN(x, y), void()) {
+    m.evalN(x, y);
+}
+template <class M, typename T, int U>
+__device__ __forceinline__ void eval_points(M& m, const T (&x)[U], T (&y)[U], long) {
+#pragma unroll
+    for (int u = 0; u < U; u++) y[u] = m.eval(x[u]);
+}
 
 // Dispatch a generic lambda-like functor F<Model> over (model_id, nmodel).
 #define MC3B_DISPATCH_MODEL(T, model_id, nmodel, CALL)                                   \

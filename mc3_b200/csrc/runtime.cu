@@ -51,6 +51,50 @@ __global__ void __launch_bounds__(256) k_fma_peak(int64_t iters, double* sink) {
 }
 }  // namespace
 
+// Variants that mimic the model kernel's operand kinds (fp64 only):
+//   1: 8 chains per thread, c operand from the constant bank / uniform registers
+//   2: 4 chains per thread (the kernel's ILP), constant operands, 6 CTAs of 128
+__device__ __constant__ double kPeakC[8] = {1e-7, 2e-7, 3e-7, 4e-7, 5e-7, 6e-7, 7e-7, 8e-7};
+template <int NCH>
+__global__ void k_fma_const(int64_t iters, double* sink) {
+    double a[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; k++) a[k] = (double)(threadIdx.x + k) * 1e-3;
+    const double m = 0.999999 + 1e-9 * threadIdx.x;
+    for (int64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+            for (int k = 0; k < NCH; k++) a[k] = fma(a[k], m, kPeakC[j]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < NCH; k++) s += a[k];
+    if (s == 123456.789) sink[0] = s;
+}
+
+extern "C" int mc3b_fma_peak_variant(int variant, int64_t iters, double* sink, double* flops, void* stream) {
+    MC3B_CHECK_ARG(sink && flops && iters > 0, "bad arguments");
+    int sms = mc3b_sm_count();
+    MC3B_CHECK_ARG(sms > 0, "no CUDA device");
+    if (variant == 1) {
+        k_fma_const<8><<<sms * 8, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+        *flops = 2.0 * 8.0 * 8.0 * 256.0 * sms * 8.0 * (double)iters;
+    } else if (variant == 2) {
+        k_fma_const<4><<<sms * 6, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+        *flops = 2.0 * 8.0 * 4.0 * 128.0 * sms * 6.0 * (double)iters;
+    } else if (variant == 3) {
+        k_fma_const<2><<<sms * 8, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+        *flops = 2.0 * 8.0 * 2.0 * 128.0 * sms * 8.0 * (double)iters;
+    } else if (variant == 4) {
+        k_fma_const<1><<<sms * 8, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+        *flops = 2.0 * 8.0 * 1.0 * 128.0 * sms * 8.0 * (double)iters;
+    } else { mc3b_set_error("bad variant %d", variant); return MC3B_ERR_ARG; }
+    MC3B_CHECK_LAUNCH("k_fma_const");
+    return MC3B_OK;
+}
+
 extern "C" int mc3b_fma_peak(int dtype, int64_t iters, double* sink, double* flops, void* stream) {
     MC3B_CHECK_ARG(sink && flops && iters > 0, "bad arguments");
     int sms = mc3b_sm_count();

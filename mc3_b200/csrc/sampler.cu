@@ -231,6 +231,32 @@ __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kicko
 
 __global__ void k_advance(int64_t* gen_dev) { *gen_dev += 1; }
 
+// log_prior of history rows (mc3/stats/stats.py:367-392) and the data chi-squared
+// it implies: lpr = -0.5 sum_j t_j^2 with t_j = (z-prior)/low|up for Gaussian
+// priors (low, up > 0), t_j = 2 log z where priorlow < 0; chisq = -2 (log_post - lpr).
+__global__ void __launch_bounds__(128) k_log_prior(const double* Z, int64_t nrows, int nfree, const int32_t* ifree,
+                                                   const double* prior, const double* plo, const double* pup,
+                                                   const double* log_post, double* lpr, double* chisq) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double acc = 0.0;
+    for (int j = 0; j < nfree; j++) {
+        const int k = ifree[j];
+        const double z = Z[r * nfree + j], lo = plo[k], up = pup[k];
+        double t = 0.0;
+        if (lo > 0.0 && up > 0.0) {
+            const double d = z - prior[k];
+            t = d < 0.0 ? d / lo : (d > 0.0 ? d / up : d);
+        } else if (lo < 0.0) {
+            t = 2.0 * log(z);
+        }
+        acc += t * t;
+    }
+    const double v = -0.5 * acc;
+    if (lpr) lpr[r] = v;
+    if (chisq) chisq[r] = -2.0 * (log_post[r] - v);
+}
+
 // ---- Gelman-Rubin ----------------------------------------------------------
 // Stage 1: one thread per (chain, parameter): mean and population variance of
 // its niter samples (two passes, as numpy's var).  Stage 2: one CTA, fixed-order
@@ -342,6 +368,18 @@ extern "C" int mc3b_advance(const mc3b_sampler_t* s, void* stream) {
     MC3B_CHECK_ARG(s && s->gen_dev, "no device generation counter");
     k_advance<<<1, 1, 0, (cudaStream_t)stream>>>(s->gen_dev);
     MC3B_CHECK_LAUNCH("k_advance");
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_log_prior(const double* Z, int64_t nrows, int nfree, const int32_t* ifree, const double* prior,
+                              const double* priorlow, const double* priorup, const double* log_post, double* lpr,
+                              double* chisq, void* stream) {
+    MC3B_CHECK_ARG(Z && ifree && prior && priorlow && priorup && nrows > 0 && nfree > 0, "bad arguments");
+    MC3B_CHECK_ARG((lpr || chisq) && (!chisq || log_post), "need an output (chisq needs log_post)");
+    k_log_prior<<<(unsigned)ceil_div64(nrows, 128), 128, 0, (cudaStream_t)stream>>>(Z, nrows, nfree, ifree, prior,
+                                                                                     priorlow, priorup, log_post,
+                                                                                     lpr, chisq);
+    MC3B_CHECK_LAUNCH("k_log_prior");
     return MC3B_OK;
 }
 

@@ -141,6 +141,7 @@ class Population:
         self.best_gen = torch.zeros(n, dtype=torch.int64, device=self.dev)
         self.gen_dev = torch.zeros(1, dtype=torch.int64, device=self.dev)
         self.gen = 0                      # generations completed
+        self.first_valid = self.M0        # first history row that is a chain sample
         self.bestp0 = np.copy(params)     # best of the initial population
         self.best_log_post0 = -np.inf
 
@@ -474,6 +475,44 @@ class Population:
                 bestp[s] = bestp[-int(self.pstep[s]) - 1]
         return dict(numaccept=numaccept, outbounds=oob.cpu().numpy().astype(int),
                     bestp=bestp, best_log_post=-0.5*best_chisq)
+
+    def history_host(self):
+        """(posterior, zchain, log_post, chisq) of the valid rows as numpy arrays;
+        chisq = -2 (log_post - log_prior) comes from the device (mc3b_log_prior)."""
+        self.gather_history()
+        lo, hi = self.first_valid, self.zsize()
+        if hi <= lo:
+            z = np.zeros((0, self.nfree))
+            return z, np.zeros(0, int), np.zeros(0), np.zeros(0)
+        chisq = torch.empty(hi - lo, dtype=torch.float64, device=self.dev)
+        _lib.call('mc3b_log_prior', self.Z[lo:hi].data_ptr(), hi - lo, self.nfree,
+                  self.d_ifree.data_ptr(), self.d_prior.data_ptr(),
+                  self.d_priorlow.data_ptr(), self.d_priorup.data_ptr(),
+                  self.log_post[lo:hi].data_ptr(), None, chisq.data_ptr(),
+                  _lib.stream_ptr())
+        self.launches += 1
+        return (self.Z[lo:hi].cpu().numpy(), self.zchain[lo:hi].cpu().numpy().astype(int),
+                self.log_post[lo:hi].cpu().numpy(), chisq.cpu().numpy())
+
+    def sample_statistics(self, zburn, quantile=0.683):
+        """median, mean, std and central-quantile bounds of the burned posterior,
+        per free parameter, computed on the device over the lock-step block of
+        rows after burn-in (stats.py:764-802 'med_central'; numpy's linear
+        percentile rule).  Sorting is torch.sort: post-processing, not the hot path."""
+        lo, hi = self.M0 + zburn*self.nchains, self.zsize()
+        blk = self.Z[lo:hi]
+        n = blk.shape[0]
+        srt, _ = torch.sort(blk, dim=0)
+
+        def pct(q):
+            pos = q*(n - 1)
+            i0 = int(np.floor(pos))
+            i1 = min(i0 + 1, n - 1)
+            fr = pos - i0
+            return (srt[i0] + (srt[i1] - srt[i0])*fr).cpu().numpy()
+        return (pct(0.5), blk.mean(dim=0).cpu().numpy(),
+                blk.std(dim=0, unbiased=False).cpu().numpy(),
+                pct(0.5*(1 - quantile)), pct(0.5*(1 + quantile)))
 
     def gelman_rubin(self, zburn):
         """PSRF per free parameter over the thinned samples after burn-in."""

@@ -53,22 +53,17 @@ def calc_bestfit_statistics(bestp, pop):
 
 
 def update_output(output, pop, hsize, counters=None):
-    """stats.py:805-852 -- fill the output dict from the device state."""
-    pop.gather_history()
+    """stats.py:805-852 -- fill the output dict from the device state.  The
+    chi-squared column and, for a lock-step history, the burned-sample
+    statistics are computed on the device; only results travel to the host."""
     zburn = output['burnin']
-    n = pop.zsize()
-    Z = pop.Z[:n].cpu().numpy()
-    zchain = pop.zchain[:n].cpu().numpy().astype(int)
-    log_post = pop.log_post[:n].cpu().numpy()
+    Z, zchain, log_post, chisq = pop.history_host()
     c = counters or pop.counters()
-    zvalid = zchain >= 0
-    nsample = np.sum(zvalid)*pop.thinning
-    lpr = ms.log_prior(Z[zvalid], pop.prior, pop.priorlow, pop.priorup, pop.pstep) \
-        if np.any(zvalid) else np.zeros(0)
-    output['posterior'] = Z[zvalid]
-    output['zchain'] = zchain[zvalid]
-    output['chisq'] = -2.0*(log_post[zvalid] - lpr)
-    output['log_post'] = log_post[zvalid]
+    nsample = zchain.size*pop.thinning
+    output['posterior'] = Z
+    output['zchain'] = zchain
+    output['chisq'] = chisq
+    output['log_post'] = log_post
     output['acceptance_rate'] = c['numaccept']*100.0/max(nsample, 1)
     bestp = c['bestp']
     best = calc_bestfit_statistics(bestp, pop)
@@ -78,12 +73,19 @@ def update_output(output, pop, hsize, counters=None):
      output['stddev_residuals']) = best
     if not pop.thinned_done() > zburn:
         return None
-    posterior, _, zmask = mu.burn(Z=Z[zvalid], zchain=zchain[zvalid], burnin=zburn)
-    st = ms.calc_sample_statistics(posterior, bestp, pop.pstep)
+    if pop.first_valid == pop.M0:          # lock-step layout: closed-form burn mask
+        K, n = pop.thinned_done(), pop.nchains
+        zmask = (np.arange(zburn, K)[None, :]*n + np.arange(n)[:, None]).ravel()
+        st = ms.expand_free_stats(pop.sample_statistics(zburn), bestp, pop.pstep)
+        nburned = zmask.size
+    else:                                  # resumed history: general host path
+        posterior, _, zmask = mu.burn(Z=Z, zchain=zchain, burnin=zburn)
+        st = ms.calc_sample_statistics(posterior, bestp, pop.pstep)
+        nburned = len(posterior)
     output['zmask'] = zmask
     (output['medianp'], output['meanp'], output['stdp'],
      output['median_low_bounds'], output['median_high_bounds']) = st
-    return posterior
+    return nburned
 
 
 def mcmc(data, uncert, func, params, indparams, indparams_dict,
@@ -181,10 +183,10 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
                     f"threshold of {grbreak:g}, stopping the MCMC.")
                 break
 
-    posterior = update_output(output, pop, hsize)
+    nburned = update_output(output, pop, hsize)
     Z = output['posterior']
     nsample = len(Z)*thinning
-    nzsample = 0 if posterior is None else len(posterior)
+    nzsample = 0 if nburned is None else nburned
     fmt = len(str(nsample))
     log.msg('\nMCMC Summary:\n-------------')
     log.msg(
@@ -216,3 +218,4 @@ def _resume(pop, oldrun):
     pop.bestp0 = np.array(oldrun['bestp'], float)
     pop.best_log_post0 = float(oldrun['best_log_post'])
     pop.resumed_accept = int(float(oldrun['acceptance_rate'])/100.0*M0)
+    pop.first_valid = 0

@@ -269,6 +269,23 @@ def marginal_statistics(posterior, statistics='med_central', quantile=0.683,
     return values, low, high
 
 
+def expand_free_stats(free_stats, bestp, pstep):
+    """Spread per-free-parameter statistics (median, mean, std, low, high[, mode,
+    hpd_low, hpd_high]) over the full parameter vector: fixed parameters keep
+    bestp (std 0), shared ones copy their source (stats.py:908-964)."""
+    pstep = np.asarray(pstep)
+    ifree = np.where(pstep > 0)[0]
+    ishare = np.where(pstep < 0)[0]
+    out = []
+    for idx, vals in enumerate(free_stats):
+        full = np.zeros(len(pstep)) if idx == 2 else np.copy(bestp).astype(float)
+        full[ifree] = vals
+        for i in ishare:
+            full[i] = full[-int(pstep[i]) - 1]
+        out.append(full)
+    return tuple(out)
+
+
 def calc_sample_statistics(posterior, bestp, pstep, quantile=0.683,
                            calc_hpd=False, pdf=None, xpdf=None):
     """median, mean, std, central bounds (+ mode and HPD bounds), expanded to

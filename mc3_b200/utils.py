@@ -89,6 +89,17 @@ def burn(Zdict=None, burnin=None, Z=None, zchain=None, sort=True):
         if burnin is None:
             burnin = Zdict['burnin']
     zchain = np.asarray(zchain)
+    # Lock-step history (row k*nchains + c holds sample k of chain c): closed form.
+    n = int(zchain.max()) + 1 if zchain.size else 0
+    if n > 0 and zchain.size % n == 0 and zchain[0] == 0 and \
+            np.array_equal(zchain.reshape(-1, n), np.broadcast_to(np.arange(n), (zchain.size//n, n))):
+        K = zchain.size//n
+        b = min(int(burnin), K)
+        if sort:
+            zmask = (np.arange(b, K)[None, :]*n + np.arange(n)[:, None]).ravel()
+        else:
+            zmask = np.arange(b*n, K*n)
+        return Z[zmask], zchain[zmask], zmask
     # rank of each sample within its own chain, vectorised over chains
     order = np.argsort(zchain, kind='stable')
     zs = zchain[order]

@@ -200,6 +200,19 @@ def test_sample_api_contract(mc3, tmp_path):
     np.testing.assert_allclose(
         out['best_chisq'],
         ok.chisq(om.polynomial(out['bestp'], p['x']), p['data'], p['uncert']), rtol=1e-9)
+    # device-side chi-squared column and burned-sample statistics == host formulas
+    prior = np.array([1.0, 0, 0, 0, 0])
+    plo = np.array([0.05, 0, 0, 0, 0])
+    lpr = ok.log_prior(out['posterior'], prior, plo, plo, p['pstep'])
+    np.testing.assert_allclose(out['chisq'], -2.0*(out['log_post'] - lpr), rtol=1e-12)
+    post, zc, zmask = mc3.utils.burn(out)
+    assert np.array_equal(zmask, out['zmask'])
+    want = mc3.stats.calc_sample_statistics(post, out['bestp'], p['pstep'])
+    # (sample() later overwrites these keys with the 20000-row-subsample values;
+    # here all rows are used, so both agree)
+    for k, wv in zip(('medianp', 'meanp', 'stdp', 'median_low_bounds',
+                      'median_high_bounds'), want):
+        np.testing.assert_allclose(out[k], wv, rtol=1e-12, atol=1e-15)
 
 
 def test_user_callables_numpy_and_torch(mc3):
