@@ -340,7 +340,12 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing NCCL down while captured graphs still reference the communicator
+        # can block; everything is reported, so leave without running destructors.
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def _profile_summary():

@@ -1,0 +1,231 @@
+#!/usr/bin/env python
+"""Measurements of the other BASELINE.json configurations (bench.py stays on
+config 2, the configuration the headline metric is quoted on).
+
+    python bench_configs.py config3 [--chains 16384] [--steps 20]
+    python bench_configs.py config4 [--n 100000000]
+    python bench_configs.py config1
+
+Each prints one JSON line: device-timed throughput (CUDA events), the roofline
+of the dominant kernel, and a bounded CPU sample of the oracle / reference C code.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'note': 'fallback'}
+
+
+def fp64_peak(torch, _lib):
+    sink = torch.zeros(8, dtype=torch.float64, device='cuda')
+    fl = ctypes.c_double()
+    best = 0.0
+    for it in range(4):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.call('mc3b_fma_peak', _lib.F64, 20000, sink.data_ptr(), ctypes.byref(fl),
+                  _lib.stream_ptr())
+        b.record()
+        torch.cuda.synchronize()
+        if it:
+            best = max(best, fl.value/(a.elapsed_time(b)*1e-3))
+    return best
+
+
+def timed(torch, fn, reps=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def config3(args):
+    import torch
+    import mc3_b200 as mc3
+    from mc3_b200 import _lib, workloads
+    from mc3_b200.engine import Population
+    w = workloads.config3()
+    n = w['x'].size
+    nch = args.chains
+    K = args.steps
+    pop = Population(w['data'], w['uncert'], mc3.models.box, w['params'], [w['x']], {},
+                     w['pstep'], w['pmin'], w['pmax'], w['prior'], w['priorlow'],
+                     w['priorup'], nchains=nch, sampler='snooker', wlike=True,
+                     thinning=1, nzchain=K + 4, seed=5, hsize=args.hsize)
+    t0 = time.perf_counter()
+    pop.init_population('normal')
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+    pop.run(3)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+    for k in range(K):
+        ev[k][0].record()
+        pop.run(1)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    P = pop.nextp
+    kms, _ = timed(torch, lambda: pop.data_chisq(P), reps=5, warm=1)
+    peak = fp64_peak(torch, _lib)
+    flops = float(w['flops_per_point'])*nch*n
+    c = pop.counters()
+    # CPU: the reference's own dwt_chisq (oracle/_ref) on one chain, numpy box model
+    from oracle import kernels as ok, models as om
+    p = w['params']
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        ok.dwt_chisq(om.box(p[:4], w['x']), w['data'], p)
+    cpu_eval = (time.perf_counter() - t0)/reps
+    line = {
+        'metric': 'chain-steps/s', 'value': nch*K/(ms*1e-3), 'unit': 'chain-steps/s',
+        'n_gpus': 1, 'steps': K, 'ms_per_step': ms/K, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': w['name'], 'nchains': nch, 'ndata': n, 'sampler': 'snooker',
+                   'wlike': True, 'hsize': args.hsize},
+        'chisq_evals_per_s': nch*K/(ms*1e-3)*n,
+        'init_population_s': t_init,
+        'acceptance_rate_pct': 100.0*c['numaccept']/(nch*(K + 3)),
+        'roofline': {'bound': 'fp64', 'kernel': 'k_dwt_pass + k_dwt_last (mc3b_dwt_chisq)',
+                     'achieved': flops/(kms*1e-3)/1e12, 'peak': peak/1e12, 'unit': 'TFLOP/s',
+                     'frac': flops/(kms*1e-3)/peak, 'ms_per_launch_set': kms,
+                     'algorithmic_flops_per_chain_point': w['flops_per_point']},
+        'cpu_baseline': {'value': 1.0/cpu_eval, 'unit': 'chain-steps/s', 'cores': 1,
+                         'kind': 'port', 'sample': f'oracle C dwt_chisq + numpy box model, one '
+                         f'chain, N=2^20: {1e3*cpu_eval:.1f} ms per evaluation'},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config4(args):
+    import torch
+    import mc3_b200 as mc3
+    from mc3_b200 import _lib
+    from oracle import problems as pb, kernels as ok
+    n = args.n
+    rs = np.random.RandomState(20260104)
+    t0 = time.perf_counter()
+    white = rs.normal(0.0, 1.0, n)
+    from scipy.signal import lfilter
+    red = lfilter([1.0], [1.0, -0.95], rs.normal(0.0, 0.2, n))
+    series = white + red
+    unc = np.abs(rs.normal(0.0, 1.0, n)) + 0.5
+    gen_s = time.perf_counter() - t0
+    dev = torch.device('cuda')
+    d = torch.from_numpy(series).to(dev)
+    u = torch.from_numpy(unc).to(dev)
+    st = _lib.stream_ptr
+    hbm = peaks().get('hbm_gbs', 6650.0)
+    out = {'metric': 'time_avg + bin_array', 'n': n, 'unit': 'ms', 'data': 'synthetic',
+           'config': {'workload': 'config4: rms-vs-binsize (maxbins 1000) + bin_array(100) on a '
+                                  f'{n:.0e}-point white+AR(1) series', 'host_generation_s': gen_s}}
+    # bin_array
+    nb = n//100
+    bd = torch.empty(nb, dtype=torch.float64, device=dev)
+    bs = torch.empty(nb, dtype=torch.float64, device=dev)
+    for name, fn, nbytes in (
+        ('bin_array_unweighted', lambda: _lib.call('mc3b_binarray', d.data_ptr(), n, 100, None,
+                                                   bd.data_ptr(), None, st()), 8.0*n + 8.0*nb),
+        ('bin_array_weighted', lambda: _lib.call('mc3b_binarray', d.data_ptr(), n, 100, u.data_ptr(),
+                                                 bd.data_ptr(), bs.data_ptr(), st()), 16.0*n + 16.0*nb)):
+        med, mn = timed(torch, fn)
+        out[name] = {'ms': med, 'ms_min': mn,
+                     'roofline': {'bound': 'hbm', 'achieved': nbytes/(med*1e-3)/1e9, 'peak': hbm,
+                                  'unit': 'GB/s', 'frac': nbytes/(med*1e-3)/1e9/hbm,
+                                  'algorithmic_bytes': nbytes}}
+    # time_avg
+    maxbins, binstep = 1000, 1
+    nout = (maxbins - 1)//binstep + 1
+    lib = _lib.load()
+    ws = torch.empty(lib.mc3b_binrms_workspace(n, maxbins, binstep)//8, dtype=torch.float64, device=dev)
+    outs = [torch.empty(nout, dtype=torch.float64, device=dev) for _ in range(5)]
+    med, mn = timed(torch, lambda: _lib.call('mc3b_binrms', d.data_ptr(), n, maxbins, binstep,
+                                             ws.data_ptr(), *[o.data_ptr() for o in outs], st()))
+    # algorithmic traffic of this formulation: read x twice (prefix, deviations), write + gather P
+    nbins_total = float(sum(n//b for b in range(1, maxbins + 1, binstep)))
+    out['time_avg'] = {'ms': med, 'ms_min': mn, 'bin_sizes': nout, 'bins_evaluated': nbins_total,
+                       'roofline': {'bound': 'hbm', 'achieved': (24.0*n)/(med*1e-3)/1e9, 'peak': hbm,
+                                    'unit': 'GB/s', 'frac': (24.0*n)/(med*1e-3)/1e9/hbm,
+                                    'algorithmic_bytes': 24.0*n,
+                                    'note': 'streaming part only (2 reads of x + 1 write of the prefix); '
+                                            'the bin gathers add 2-4 sector reads per bin'}}
+    # parity at full size against direct sums (a few bin sizes) and oracle on a prefix
+    rms = outs[0].cpu().numpy()
+    err = outs[3].cpu().numpy()
+    chk = {}
+    for i in (0, 9, 99, 499, 999):
+        b = 1 + i*binstep
+        M = n//b
+        means = series[:M*b].reshape(M, b).mean(axis=1)
+        chk[b] = abs(rms[i]/np.sqrt(np.mean(means**2)) - 1.0)
+    out['time_avg']['max_rel_err_vs_direct'] = max(chk.values())
+    # CPU baselines (bounded): reference C binarray on the full series, binrms on 2e6 points
+    t0 = time.perf_counter(); ok.bin_array(series, 100); t_ba = time.perf_counter() - t0
+    t0 = time.perf_counter(); ok.bin_array(series, 100, unc); t_baw = time.perf_counter() - t0
+    ns = min(n, 2_000_000)
+    t0 = time.perf_counter(); ok.time_avg(series[:ns], 1000, 1); t_ta = time.perf_counter() - t0
+    out['cpu_baseline'] = {'kind': 'port', 'cores': 1,
+                           'bin_array_unweighted_ms': 1e3*t_ba, 'bin_array_weighted_ms': 1e3*t_baw,
+                           'time_avg_ms_extrapolated': 1e3*t_ta*n/ns,
+                           'sample': f'oracle C binarray on all {n} points; oracle C binrms on the first '
+                                     f'{ns} points ({t_ta:.2f} s), scaled linearly in N'}
+    print(json.dumps(out), flush=True)
+
+
+def config1(args):
+    """examples/get_started.py as written: snooker, 7 chains, 1e5 samples."""
+    import torch
+    import mc3_b200 as mc3
+    from oracle import problems as pb
+    p = pb.mcmc_case('quad')
+    quiet = mc3.Log(verb=-1)
+    res = {}
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = mc3.sample(p['data'], p['uncert'], func=mc3.models.polynomial, params=p['params'],
+                         indparams=[p['x']], pstep=p['pstep'], sampler='snooker', nsamples=1e5,
+                         burnin=1000, nchains=7, seed=3, log=quiet)
+        torch.cuda.synchronize()
+        res[rep] = time.perf_counter() - t0
+    line = {'metric': 'chain-steps/s', 'value': 100002/res[1], 'unit': 'chain-steps/s',
+            'config': {'workload': 'config1: get_started quadratic, snooker, 7 chains, N=100, 1e5 samples'},
+            'seconds': res[1], 'seconds_first_call': res[0],
+            'bestp': out['bestp'].tolist(), 'best_chisq': float(out['best_chisq']),
+            'medianp': out['medianp'].tolist(), 'acceptance_rate': float(out['acceptance_rate']),
+            'reference_docs': {'bestp': [3.0768, -2.5000, 0.5089], 'best_chisq': 112.5923,
+                               'acceptance_rate': 28.36, 'seconds': 6.0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    ap = argparse.ArgumentParser()
+    ap.add_argument('which', choices=['config1', 'config3', 'config4'])
+    ap.add_argument('--chains', type=int, default=16384)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--hsize', type=int, default=10)
+    ap.add_argument('--n', type=int, default=100_000_000)
+    a = ap.parse_args()
+    {'config1': config1, 'config3': config3, 'config4': config4}[a.which](a)
