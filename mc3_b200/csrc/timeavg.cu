@@ -11,8 +11,8 @@
 // to build P.  Local prefixes keep the magnitudes small: bin sums agree with
 // the reference's direct sums to ~1e-14 relative.  Reductions are fixed-order.
 //
-// binarray: HBM-bound streaming; a CTA stages a contiguous run of whole bins in
-// shared memory with coalesced loads, one warp reduces each bin.
+// binarray: HBM-bound streaming; one warp per bin with coalesced loads (measured
+// faster than shared-memory staging, plain or TMA: see profiles/).
 #include "common.cuh"
 
 namespace {
@@ -36,7 +36,8 @@ __device__ __forceinline__ double block_sum_256(double v, double* sh) {
     return t;
 }
 
-// P = block-local inclusive prefix; tot[b] = block total.
+// P = block-local inclusive prefix (when WRITEP); tot[b] = block total.
+template <bool WRITEP>
 __global__ void __launch_bounds__(256) k_block_prefix(const double* x, int64_t n, double* P, double* tot) {
     __shared__ double wsum[8];
     const int64_t base = (int64_t)blockIdx.x * PB + threadIdx.x * 4;
@@ -55,9 +56,11 @@ __global__ void __launch_bounds__(256) k_block_prefix(const double* x, int64_t n
     double woff = 0.0;
     for (int k = 0; k < warp; k++) woff += wsum[k];
     const double excl = woff + run - v[3];
+    if (WRITEP) {
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (base + k < n) P[base + k] = v[k] + excl;
+        for (int k = 0; k < 4; k++)
+            if (base + k < n) P[base + k] = v[k] + excl;
+    }
     if (threadIdx.x == 255) tot[blockIdx.x] = woff + run;
 }
 
@@ -122,10 +125,10 @@ __device__ __forceinline__ double range_sum(const double* P, const double* T2, i
 }
 
 // grid (bin-size index, split): partial[y, i] = sum over this split's bins of mean^2.
-__global__ void __launch_bounds__(256) k_binrms_main(const double* P, const double* T2, int64_t n, int64_t nout,
-                                                    int64_t binstep, double* partial) {
+__global__ void __launch_bounds__(256) k_binrms_main(const double* P, const double* T2, int64_t n, int64_t i_begin,
+                                                    int64_t nout, int64_t binstep, double* partial) {
     __shared__ double sh[9];
-    for (int64_t i = blockIdx.x; i < nout; i += gridDim.x) {
+    for (int64_t i = i_begin + blockIdx.x; i < nout; i += gridDim.x) {
         const int64_t b = 1 + i * binstep, M = n / b;
         const int64_t j0 = M * blockIdx.y / gridDim.y, j1 = M * (blockIdx.y + 1) / gridDim.y;
         const double inv = 1.0 / (double)b;
@@ -137,6 +140,83 @@ __global__ void __launch_bounds__(256) k_binrms_main(const double* P, const doub
         a = block_sum_256(a, sh);
         if (threadIdx.x == 0) partial[(int64_t)blockIdx.y * nout + i] = a;
     }
+}
+
+// Tile version for the small bin sizes (b <= BMAX): a persistent CTA stages a
+// tile of TT owned points + a halo of (largest small bin - 1) points in shared
+// memory with one TMA bulk copy, turns it into an inclusive prefix in place, and
+// evaluates EVERY small bin size from it (a bin belongs to the tile its first
+// point is in).  HBM traffic is one pass over the series (+ halo) instead of 2-4
+// sectors per bin.  acc[i] (shared) collects sum of mean^2 per bin size over
+// the CTA's tiles in a fixed order; partial[cta, i] leaves at the end.
+constexpr int TT = 8192;
+constexpr int BMAX = 4096;
+
+__global__ void __launch_bounds__(256) k_binrms_tile(const double* x, int64_t n, int64_t nsmall, int64_t binstep,
+                                                    int halo, int64_t nout, double* partial) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double wsum[8];
+    double* P = sm;                              // [TT + halo]
+    double* acc = sm + TT + halo;                // [nsmall]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t i = threadIdx.x; i < nsmall; i += 256) acc[i] = 0.0;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    const int64_t ntiles = (n + TT - 1) / TT;
+    uint32_t phase = 0;
+    const int len_full = TT + halo;
+    const int per = (len_full + 255) / 256;      // elements per thread in the scan
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t t0 = t * TT;
+        const int len = (int)((n - t0) < len_full ? (n - t0) : len_full);
+        if (len == len_full) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, (uint32_t)len_full * 8u);
+                bulk_g2s(P, x + t0, (uint32_t)len_full * 8u, &bar);
+            }
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        } else {
+            for (int k = threadIdx.x; k < len; k += 256) P[k] = x[t0 + k];
+            __syncthreads();
+        }
+        // inclusive prefix of P[0..len) in place
+        const int k0 = threadIdx.x * per, k1 = (k0 + per < len) ? k0 + per : len;
+        double run = 0.0;
+        for (int k = k0; k < k1; k++) { run += P[k]; P[k] = run; }
+        double sc = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, sc, o);
+            if (lane >= o) sc += v;
+        }
+        if (lane == 31) wsum[warp] = sc;
+        __syncthreads();
+        double off = sc - run;
+        for (int k = 0; k < warp; k++) off += wsum[k];
+        for (int k = k0; k < k1; k++) P[k] += off;
+        __syncthreads();
+        // bins: warp w takes bin sizes i = w, w+8, ...
+        const int64_t own_end = (t0 + TT < n) ? t0 + TT : n;
+        for (int64_t i = warp; i < nsmall; i += 8) {
+            const int64_t b = 1 + i * binstep, M = n / b;
+            int64_t j0 = (t0 + b - 1) / b;                          // first bin starting in the tile
+            int64_t j1 = (own_end + b - 1) / b;                     // one past the last such bin
+            if (j1 > M) j1 = M;
+            const double inv = 1.0 / (double)b;
+            double a = 0.0;
+            for (int64_t j = j0 + lane; j < j1; j += 32) {
+                const int ls = (int)(j * b - t0), le = ls + (int)b;
+                const double sum = P[le - 1] - (ls > 0 ? P[ls - 1] : 0.0);
+                const double m = sum * inv;
+                a = fma(m, m, a);
+            }
+            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+            if (lane == 0) acc[i] += a;
+        }
+        __syncthreads();                         // tile buffer free again
+    }
+    for (int64_t i = threadIdx.x; i < nsmall; i += 256) partial[(int64_t)blockIdx.x * nout + i] = acc[i];
 }
 
 // One thread per bin size: rms, asymptotic errors, Gaussian extrapolation, and
@@ -230,51 +310,6 @@ __global__ void k_fill_int(int* p, int n, int v) {
 }
 
 // ---- binarray ---------------------------------------------------------------
-constexpr int BA_CHUNK = 4096;      // elements staged per CTA
-
-template <bool W>
-__global__ void __launch_bounds__(256) k_binarray_small(const double* d, const double* u, int64_t nbins,
-                                                       int64_t binsize, int bpc, double* bd, double* bs) {
-    constexpr int CHK = W ? BA_CHUNK / 2 : BA_CHUNK;
-    __shared__ double sd[CHK];
-    __shared__ double sw[W ? CHK : 1];
-    const int64_t bin0 = (int64_t)blockIdx.x * bpc;
-    const int nb = (int)((nbins - bin0) < bpc ? (nbins - bin0) : bpc);
-    const int64_t e0 = bin0 * binsize;
-    const int ne = nb * (int)binsize;
-    for (int k = threadIdx.x; k < ne; k += 256) {
-        if (W) {
-            const double s = u[e0 + k], w = 1.0 / (s * s);
-            sw[k] = w;
-            sd[k] = d[e0 + k] * w;
-        } else {
-            sd[k] = d[e0 + k];
-        }
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = warp; b < nb; b += 8) {
-        double a = 0.0, w = 0.0;
-        for (int k = lane; k < (int)binsize; k += 32) {
-            a += sd[b * (int)binsize + k];
-            if (W) w += sw[b * (int)binsize + k];
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (W) w += __shfl_xor_sync(0xffffffffu, w, o);
-        }
-        if (lane == 0) {
-            if (W) {
-                const double sdv = sqrt(1.0 / w);
-                bs[bin0 + b] = sdv;
-                bd[bin0 + b] = a * sdv * sdv;
-            } else {
-                bd[bin0 + b] = a / (double)binsize;
-            }
-        }
-    }
-}
-
 template <bool W>
 __global__ void __launch_bounds__(256) k_binarray_big(const double* d, const double* u, int64_t binsize, double* bd,
                                                      double* bs) {
@@ -303,19 +338,134 @@ __global__ void __launch_bounds__(256) k_binarray_big(const double* d, const dou
     }
 }
 
-struct RmsLayout { int64_t nblk, nout; int ys; int64_t oP, oTot, oT2, oDev, oPart, oIg, oLohi, oStat, oLead, words; };
+// Direct version (no staging): one warp per bin, lanes read the bin with
+// coalesced 8-byte loads (4 independent loads in flight per lane at binsize 100,
+// 64 resident warps per SM keep ~64 KB in flight), fixed-order lane tree.  Short
+// bins (< 32 points) take one thread per bin.
+// 1/v for the weights: single-precision seed + two Newton steps in fp64 (error
+// < 2 ulp, no slow-path branches); values outside the float range take the
+// exact division.
+__device__ __forceinline__ double fast_rcp(double v) {
+    if (!(v > 1e-30 && v < 1e30)) return 1.0 / v;
+    double x = (double)__frcp_rn((float)v);
+    x = x * fma(-v, x, 2.0);
+    x = x * fma(-v, x, 2.0);
+    return fma(x, fma(-v, x, 1.0), x);
+}
 
-RmsLayout rms_layout(int64_t n, int64_t maxbins, int64_t binstep) {
+template <bool W, int NB>
+__global__ void __launch_bounds__(256) k_binarray_direct(const double* __restrict__ d, const double* __restrict__ u,
+                                                        int64_t nbins, int64_t binsize, double* bd, double* bs) {
+    // NB bins per warp and pass; every lane first issues all its loads of a pass
+    // (up to 8 per bin, independent), then adds: 8*NB loads in flight per lane.
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b0 = warp * NB; b0 < nbins; b0 += nwarps * NB) {
+        double a[NB], w[NB];
+#pragma unroll
+        for (int q = 0; q < NB; q++) { a[q] = 0.0; w[q] = 0.0; }
+        for (int64_t base = 0; base < binsize; base += 256) {
+            double v[NB][8], sg[NB][8];
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                const int64_t b = b0 + q;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int64_t k = base + lane + 32 * j;
+                    const bool ok = (k < binsize) && (b < nbins);
+                    v[q][j] = ok ? d[b * binsize + k] : 0.0;
+                    if (W) sg[q][j] = ok ? u[b * binsize + k] : 1.0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (W) {
+                        const int64_t k = base + lane + 32 * j;
+                        const double ww = (k < binsize) ? fast_rcp(sg[q][j] * sg[q][j]) : 0.0;
+                        w[q] += ww;
+                        a[q] = fma(v[q][j], ww, a[q]);
+                    } else {
+                        a[q] += v[q][j];
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+            double aa = a[q], ww = w[q];
+            for (int o = 16; o > 0; o >>= 1) {
+                aa += __shfl_xor_sync(0xffffffffu, aa, o);
+                if (W) ww += __shfl_xor_sync(0xffffffffu, ww, o);
+            }
+            const int64_t b = b0 + q;
+            if (lane == 0 && b < nbins) {
+                if (W) {
+                    const double sdv = sqrt(1.0 / ww);
+                    bs[b] = sdv;
+                    bd[b] = aa * sdv * sdv;
+                } else {
+                    bd[b] = aa / (double)binsize;
+                }
+            }
+        }
+    }
+}
+
+template <bool W>
+__global__ void __launch_bounds__(256) k_binarray_short(const double* __restrict__ d, const double* __restrict__ u,
+                                                       int64_t nbins, int binsize, double* bd, double* bs) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    const double* x = d + b * binsize;
+    double a = 0.0, w = 0.0;
+    for (int k = 0; k < binsize; k++) {
+        if (W) { const double s0 = u[b * binsize + k], q0 = 1.0 / (s0 * s0); w += q0; a = fma(x[k], q0, a); }
+        else a += x[k];
+    }
+    if (W) {
+        const double sdv = sqrt(1.0 / w);
+        bs[b] = sdv;
+        bd[b] = a * sdv * sdv;
+    } else {
+        bd[b] = a / (double)binsize;
+    }
+}
+
+struct RmsLayout { int64_t nblk, nout, nsmall; int ys, rows, tile_ctas, halo; bool use_tile, need_prefix;
+                   int64_t oP, oTot, oT2, oDev, oPart, oIg, oLohi, oStat, oLead, words; };
+
+RmsLayout rms_layout(int64_t n, int64_t maxbins, int64_t binstep, bool allow_tile = true) {
     RmsLayout L;
     L.nblk = ceil_div64(n, PB);
     L.nout = (maxbins - 1) / binstep + 1;
     L.ys = (int)(n / 65536 < 1 ? 1 : (n / 65536 > YS ? YS : n / 65536));
+    // bin sizes b = 1 + i*binstep <= BMAX go to the tile kernel (large series only)
+    L.use_tile = allow_tile && n >= 262144;
+    L.nsmall = 0;
+    if (L.use_tile) {
+        const int64_t bcap = maxbins < BMAX ? maxbins : BMAX;
+        L.nsmall = (bcap - 1) / binstep + 1;
+        if (L.nsmall > L.nout) L.nsmall = L.nout;
+    }
+    const int64_t bsmall = L.nsmall > 0 ? 1 + (L.nsmall - 1) * binstep : 1;
+    L.halo = (int)(((bsmall - 1) + 1) & ~1LL);                 // even: whole 16-byte units
+    int sms = mc3b_sm_count();
+    if (sms <= 0) sms = 148;
+    const size_t tile_smem = (size_t)(TT + L.halo + L.nsmall) * 8;
+    L.tile_ctas = sms * (tile_smem <= 100 * 1024 ? 2 : 1);
+    const int64_t ntiles = ceil_div64(n, TT);
+    if (L.tile_ctas > ntiles) L.tile_ctas = (int)ntiles;
+    L.need_prefix = L.nsmall < L.nout;
+    L.rows = L.use_tile ? (L.tile_ctas > L.ys ? L.tile_ctas : L.ys) : L.ys;
     int64_t o = 0;
-    L.oP = o; o += n;
+    L.oP = o; o += n;                 // always reserved: the launch may fall back to the prefix path
     L.oTot = o; o += L.nblk;
     L.oT2 = o; o += L.nblk + 1;
     L.oDev = o; o += L.nblk;
-    L.oPart = o; o += (int64_t)L.ys * L.nout;
+    L.oPart = o; o += (int64_t)L.rows * L.nout;
     L.oIg = o; o += (int64_t)36 * 3 * IGN;
     L.oLohi = o; o += 72;
     L.oStat = o; o += 2;
@@ -340,12 +490,14 @@ extern "C" int mc3b_binrms(const double* data, int64_t n, int64_t maxbins, int64
     MC3B_CHECK_ARG(n > 0 && binstep > 0 && maxbins >= 1 && maxbins <= n, "bad sizes (n=%lld maxbins=%lld binstep=%lld)",
                    (long long)n, (long long)maxbins, (long long)binstep);
     cudaStream_t st = (cudaStream_t)stream;
-    const RmsLayout L = rms_layout(n, maxbins, binstep);
+    const bool aligned = ((uintptr_t)data & 15) == 0;     // the tile kernel's bulk copies need it
+    const RmsLayout L = rms_layout(n, maxbins, binstep, aligned);
     double* w = (double*)workspace;
     double *P = w + L.oP, *tot = w + L.oTot, *T2 = w + L.oT2, *dev = w + L.oDev, *part = w + L.oPart;
     double *ig = w + L.oIg, *lohi = w + L.oLohi, *stat = w + L.oStat;
     int* lead = (int*)(w + L.oLead);
-    k_block_prefix<<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
+    if (L.need_prefix) k_block_prefix<true><<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
+    else k_block_prefix<false><<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
     MC3B_CHECK_LAUNCH("k_block_prefix");
     k_totals_scan<<<1, 256, 0, st>>>(tot, L.nblk, n, T2, stat);
     MC3B_CHECK_LAUNCH("k_totals_scan");
@@ -353,12 +505,22 @@ extern "C" int mc3b_binrms(const double* data, int64_t n, int64_t maxbins, int64
     MC3B_CHECK_LAUNCH("k_dev2");
     k_std<<<1, 256, 0, st>>>(dev, L.nblk, n, stat);
     MC3B_CHECK_LAUNCH("k_std");
-    const unsigned gx = (unsigned)(L.nout < (1 << 20) ? L.nout : (1 << 20));
-    k_binrms_main<<<dim3(gx, (unsigned)L.ys), 256, 0, st>>>(P, T2, n, L.nout, binstep, part);
-    MC3B_CHECK_LAUNCH("k_binrms_main");
+    MC3B_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)L.rows * L.nout, st));
+    if (L.nsmall > 0) {
+        const size_t smem = (size_t)(TT + L.halo + L.nsmall) * 8;
+        MC3B_CUDA(cudaFuncSetAttribute(k_binrms_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_binrms_tile<<<(unsigned)L.tile_ctas, 256, smem, st>>>(data, n, L.nsmall, binstep, L.halo, L.nout, part);
+        MC3B_CHECK_LAUNCH("k_binrms_tile");
+    }
+    if (L.need_prefix) {
+        const int64_t nbig = L.nout - L.nsmall;
+        const unsigned gx = (unsigned)(nbig < (1 << 20) ? nbig : (1 << 20));
+        k_binrms_main<<<dim3(gx, (unsigned)L.ys), 256, 0, st>>>(P, T2, n, L.nsmall, L.nout, binstep, part);
+        MC3B_CHECK_LAUNCH("k_binrms_main");
+    }
     k_fill_int<<<1, 64, 0, st>>>(lead, 36, -1);
     MC3B_CHECK_LAUNCH("k_fill_int");
-    k_binrms_finish<<<(unsigned)ceil_div64(L.nout, 128), 128, 0, st>>>(part, L.ys, n, L.nout, binstep, stat, rms,
+    k_binrms_finish<<<(unsigned)ceil_div64(L.nout, 128), 128, 0, st>>>(part, L.rows, n, L.nout, binstep, stat, rms,
                                                                         rmslo, rmshi, stderr_, binsz, lead);
     MC3B_CHECK_LAUNCH("k_binrms_finish");
     if (n / (1 + (L.nout - 1) * binstep) <= 35) {        // some bin size has <= 35 bins
@@ -378,16 +540,32 @@ extern "C" int mc3b_binarray(const double* data, int64_t n, int64_t binsize, con
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nbins = n / binsize;
     if (nbins == 0) return MC3B_OK;
-    const int64_t chunk = uncert ? BA_CHUNK / 2 : BA_CHUNK;
-    if (binsize <= chunk / 2) {
-        const int bpc = (int)(chunk / binsize);
-        const unsigned grid = (unsigned)ceil_div64(nbins, bpc);
-        if (uncert) k_binarray_small<true><<<grid, 256, 0, st>>>(data, uncert, nbins, binsize, bpc, bindata, binstd);
-        else k_binarray_small<false><<<grid, 256, 0, st>>>(data, uncert, nbins, binsize, bpc, bindata, binstd);
-    } else {
-        if (uncert) k_binarray_big<true><<<(unsigned)nbins, 256, 0, st>>>(data, uncert, binsize, bindata, binstd);
-        else k_binarray_big<false><<<(unsigned)nbins, 256, 0, st>>>(data, uncert, binsize, bindata, binstd);
+    if (binsize < 32) {
+        const unsigned grid = (unsigned)ceil_div64(nbins, 256);
+        if (uncert) k_binarray_short<true><<<grid, 256, 0, st>>>(data, uncert, nbins, (int)binsize, bindata, binstd);
+        else k_binarray_short<false><<<grid, 256, 0, st>>>(data, uncert, nbins, (int)binsize, bindata, binstd);
+        MC3B_CHECK_LAUNCH("k_binarray_short");
+        return MC3B_OK;
     }
+    if (binsize <= 8192) {
+        int sms = mc3b_sm_count();
+        int64_t grid = ceil_div64(nbins, 8);               // 8 warps (bins) per CTA
+        const int64_t cap = (int64_t)sms * 8 * 16;        // grid-stride beyond 16 waves
+        if (grid > cap) grid = cap;
+        if (binsize <= 128) {                            // short bins: two per warp and pass
+            grid = ceil_div64(nbins, 16);
+            if (grid > cap) grid = cap;
+            if (uncert) k_binarray_direct<true, 2><<<(unsigned)grid, 256, 0, st>>>(data, uncert, nbins, binsize, bindata, binstd);
+            else k_binarray_direct<false, 2><<<(unsigned)grid, 256, 0, st>>>(data, uncert, nbins, binsize, bindata, binstd);
+        } else {
+            if (uncert) k_binarray_direct<true, 1><<<(unsigned)grid, 256, 0, st>>>(data, uncert, nbins, binsize, bindata, binstd);
+            else k_binarray_direct<false, 1><<<(unsigned)grid, 256, 0, st>>>(data, uncert, nbins, binsize, bindata, binstd);
+        }
+        MC3B_CHECK_LAUNCH("k_binarray_direct");
+        return MC3B_OK;
+    }
+    if (uncert) k_binarray_big<true><<<(unsigned)nbins, 256, 0, st>>>(data, uncert, binsize, bindata, binstd);
+    else k_binarray_big<false><<<(unsigned)nbins, 256, 0, st>>>(data, uncert, binsize, bindata, binstd);
     MC3B_CHECK_LAUNCH("k_binarray");
     return MC3B_OK;
 }

@@ -356,8 +356,21 @@ class Population:
                 allgather_rows(self.Z[r0:r0 + self.nchains], self.chain0,
                                self.nlocal, self.group)
 
+    def _capture(self, ngens):
+        """CUDA graph of `ngens` device-driven generations."""
+        g = torch.cuda.CUDAGraph()
+        before = self.launches
+        with torch.cuda.graph(g):
+            for _ in range(ngens):
+                self._generation(-1)
+        per = self.launches - before
+        self.launches = before
+        return g, per
+
     def run(self, ngen, use_graph=None):
-        """Advance `ngen` generations."""
+        """Advance `ngen` generations.  Built-in models replay captured CUDA
+        graphs; small problems (launch-latency bound) replay graphs that hold a
+        block of generations."""
         if ngen <= 0:
             return
         if use_graph is None:
@@ -376,13 +389,21 @@ class Population:
             self.gen_dev.fill_(self.gen)
             ngen -= 1
             torch.cuda.synchronize(self.dev)
-            g = torch.cuda.CUDAGraph()
-            before = self.launches
-            with torch.cuda.graph(g):
-                self._generation(-1)
-            self._graph_launches = self.launches - before
-            self.launches = before
-            self._graph = g
+            self._graph, self._graph_launches = self._capture(1)
+            # generations per block graph: aim at >= ~0.3 ms of device work per replay
+            work = float(self.nlocal)*self.ndata
+            self._block = 1 if work > 2e8 else (8 if work > 2e7 else 32)
+            self._block_graph = None
+        if self._block > 1 and ngen >= self._block:
+            if self._block_graph is None:
+                self._block_graph, _ = self._capture(self._block)
+            nb = ngen // self._block
+            for _ in range(nb):
+                self._block_graph.replay()
+            done = nb*self._block
+            self.launches += done*self._graph_launches
+            self.gen += done
+            ngen -= done
         for _ in range(ngen):
             self._graph.replay()
         self.launches += ngen*self._graph_launches

@@ -372,3 +372,45 @@ def test_fast_sin_accuracy(mc3):
     tiny = np.abs(xs) == 1e-300
     assert np.array_equal(got[tiny], xs[tiny])
     assert np.isnan(mc3.models.sinusoid(p, np.array([np.inf, np.nan, 1.0, 2.0])))[:2].all()
+
+
+def test_time_avg_tile_and_prefix_paths_agree_with_oracle(mc3):
+    """n large enough for the shared-memory tile kernel (bin sizes <= 4096) with
+    maxbins beyond it (global-prefix kernel for the rest), odd n, ragged tiles."""
+    n = 1_000_003
+    d = pb.series_case(n, 33) + 0.7          # non-zero mean
+    for maxbins, binstep in ((6000, 499), (1000, 1), (4096, 65), (50000, 4999)):
+        got = np.array(mc3.stats.time_avg(d, maxbins, binstep))
+        want = np.array(ok.time_avg(d, maxbins, binstep))
+        np.testing.assert_allclose(got, want, rtol=R64)
+    # unaligned input (8-byte offset): the bulk-copy path must be left
+    import torch
+    from mc3_b200 import _lib
+    dev = torch.device('cuda')
+    buf = torch.from_numpy(np.concatenate([[0.0], d])).to(dev)
+    view = buf[1:]
+    assert view.data_ptr() % 16 == 8
+    nout = 10
+    outs = [torch.empty(nout, dtype=torch.float64, device=dev) for _ in range(5)]
+    lib = _lib.load()
+    ws = torch.empty(lib.mc3b_binrms_workspace(n, 1000, 111)//8, dtype=torch.float64, device=dev)
+    _lib.call('mc3b_binrms', view.data_ptr(), n, 1000, 111, ws.data_ptr(),
+              *[o.data_ptr() for o in outs], _lib.stream_ptr())
+    want = np.array(ok.time_avg(d, 1000, 111))
+    np.testing.assert_allclose(np.array([o.cpu().numpy() for o in outs]), want, rtol=R64)
+    bd = torch.empty(n//100, dtype=torch.float64, device=dev)
+    _lib.call('mc3b_binarray', view.data_ptr(), n, 100, None, bd.data_ptr(), None,
+              _lib.stream_ptr())
+    np.testing.assert_allclose(bd.cpu().numpy(), ok.bin_array(d, 100), rtol=R64)
+
+
+@pytest.mark.parametrize('bs', [1, 2, 3, 31, 32, 33, 100, 1023, 1024, 1025, 2048])
+def test_bin_array_sizes(mc3, bs):
+    n = 300_007
+    rs = np.random.RandomState(bs)
+    d, u = rs.normal(1.0, 1.0, n), np.abs(rs.normal(0, 1, n)) + 0.5
+    np.testing.assert_allclose(mc3.stats.bin_array(d, bs), ok.bin_array(d, bs), rtol=R64)
+    gw, gs = mc3.stats.bin_array(d, bs, u)
+    ww, ws = ok.bin_array(d, bs, u)
+    np.testing.assert_allclose(gw, ww, rtol=R64)
+    np.testing.assert_allclose(gs, ws, rtol=R64)
