@@ -220,12 +220,81 @@ def config1(args):
     print(json.dumps(line), flush=True)
 
 
+def config5(args):
+    """MRW + DEMC, 65536 chains over the GPUs of one box, N = 1e6 points per GPU
+    (launch under torchrun).  --shard chains: chains partitioned, data replicated,
+    population all-gather;  --shard data: data sharded, chi-squared all-gather."""
+    import torch
+    import torch.distributed as dist
+    import mc3_b200 as mc3
+    from mc3_b200 import workloads
+    from mc3_b200.engine import Population
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    n_total = args.n5*world
+    w = workloads.config2(n=n_total, seed=20260105)
+    w['x'] = np.linspace(0, 10.0*world, n_total)
+    w['data'] = workloads.sinusoid_np(np.array([1.0, 2.5, 0.3, 5.0, -0.2]), w['x']) + \
+        np.random.RandomState(20260105).normal(0, 0.5, n_total)
+    K = args.steps
+    lines = []
+    for sampler in ('mrw', 'demc'):
+        pop = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {},
+                         w['pstep'], w['pmin'], w['pmax'], w['prior'], w['priorlow'], w['priorup'],
+                         nchains=args.chains5, sampler=sampler, fepsilon=0.01, thinning=1,
+                         nzchain=K + 4, seed=9, hsize=args.hsize, rank=rank, world=world,
+                         shard=args.shard)
+        pop.init_population('normal')
+        pop.run(3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pop.run(K)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        psrf = pop.gelman_rubin(0)
+        c = pop.counters()
+        lines.append({'sampler': sampler, 'ms_per_step': ms/K,
+                      'chain_steps_per_s': args.chains5*K/(ms*1e-3),
+                      'chisq_evals_per_s': args.chains5*K/(ms*1e-3)*n_total,
+                      'acceptance_pct': 100.0*c['numaccept']/(args.chains5*(K + 3)),
+                      'gelman_rubin_max': float(np.max(psrf))})
+        del pop
+        torch.cuda.empty_cache()
+    if rank == 0:
+        print(json.dumps({'metric': 'chain-steps/s', 'n_gpus': world, 'shard': args.shard,
+                          'config': {'workload': 'config5: 65536 chains, sinusoid+line, '
+                                     f'N={args.n5:.0e} points per GPU ({n_total:.0e} total)',
+                                     'nchains': args.chains5, 'ndata_total': n_total,
+                                     'hsize': args.hsize, 'steps': K},
+                          'runs': lines}), flush=True)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('which', choices=['config1', 'config3', 'config4'])
+    ap.add_argument('which', choices=['config1', 'config3', 'config4', 'config5'])
+    ap.add_argument('--shard', default='chains', choices=['chains', 'data'])
+    ap.add_argument('--chains5', type=int, default=65536)
+    ap.add_argument('--n5', type=int, default=1_000_000)
     ap.add_argument('--chains', type=int, default=16384)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--hsize', type=int, default=10)
     ap.add_argument('--n', type=int, default=100_000_000)
     a = ap.parse_args()
-    {'config1': config1, 'config3': config3, 'config4': config4}[a.which](a)
+    {'config1': config1, 'config3': config3, 'config4': config4, 'config5': config5}[a.which](a)

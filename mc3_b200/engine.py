@@ -45,13 +45,21 @@ class Population:
                  priorup=None, nchains=7, sampler='snooker', wlike=False,
                  fgamma=1.0, fepsilon=0.0, hsize=10, thinning=1, nzchain=1,
                  seed=0, dtype='f64', device=None, rank=0, world=1, group=None,
-                 reflect=False, M0=None):
+                 reflect=False, M0=None, shard='chains'):
         _lib.load()
         if not torch.cuda.is_available():
             raise _lib.Mc3bError('mc3_b200 needs a CUDA device (no CPU fallback)')
         self.dev = torch.device('cuda', torch.cuda.current_device()) \
             if device is None else torch.device(device)
         self.rank, self.world, self.group = rank, world, group
+        # shard='chains': each device owns a block of chains (population exchange
+        # per generation).  shard='data': each device holds a slice of the data
+        # and evaluates ALL chains on it; the per-device chi-squared sums are
+        # all-gathered and added in rank order, proposals and decisions are
+        # replicated bit for bit ("large-N variant").
+        self.shard = shard if world > 1 else 'chains'
+        if self.shard not in ('chains', 'data'):
+            raise ValueError("shard must be 'chains' or 'data'")
         self.func = func
         self.indparams = list(indparams)
         self.indparams_dict = dict(indparams_dict or {})
@@ -77,7 +85,12 @@ class Population:
         if npars > _lib.MAX_PARS:
             raise ValueError(f'at most {_lib.MAX_PARS} parameters are supported')
         self.nchains = int(nchains)
-        self.chain0, self.nlocal = chain_slice(self.nchains, rank, world)
+        if self.shard == 'data':
+            if wlike:
+                raise ValueError('the wavelet likelihood cannot be sharded over data')
+            self.chain0, self.nlocal = 0, self.nchains
+        else:
+            self.chain0, self.nlocal = chain_slice(self.nchains, rank, world)
         self.hsize, self.thinning, self.nzchain = int(hsize), int(thinning), int(nzchain)
         self.M0 = self.hsize*self.nchains if M0 is None else int(M0)
         self.zlen = self.M0 + self.nzchain*self.nchains
@@ -86,6 +99,13 @@ class Population:
         # ---- data ----
         data = np.ascontiguousarray(data, dtype=np.double)
         uncert = np.ascontiguousarray(uncert, dtype=np.double)
+        self.host_data = data              # whole series (best-fit residual statistics)
+        self.ndata_total = data.size
+        lo, hi = 0, data.size
+        if self.shard == 'data':
+            lo, hi = rank*data.size//world, (rank + 1)*data.size//world
+            data, uncert = data[lo:hi], uncert[lo:hi]
+        self.data_slice = (lo, hi)
         self.ndata = data.size
         self.d_data = torch.from_numpy(data).to(self.dev)
         self.d_uncert = torch.from_numpy(uncert).to(self.dev)
@@ -94,9 +114,10 @@ class Population:
             self.kind = 'builtin'
             self.nmodel = func.nmodel(self.nfunc)
             x = np.ascontiguousarray(self.indparams[0], dtype=np.double)
-            if x.shape != data.shape:
+            if x.size != self.ndata_total or x.ndim != 1:
                 raise ValueError('built-in models need indparams=[x] with the '
                                  'same shape as data')
+            x = x[lo:hi]
             self.d_x = torch.from_numpy(x).to(self.dev)
             self.d_invsig = 1.0/self.d_uncert
             if self.dtype == _lib.F32:
@@ -104,6 +125,8 @@ class Population:
                                                 (self.d_x, self.d_data, self.d_invsig))
             else:
                 self.k_x, self.k_d, self.k_w = self.d_x, self.d_data, self.d_invsig
+        elif self.shard == 'data':
+            raise ValueError("shard='data' needs a built-in model")
         elif isinstance(func, TorchModel):
             self.kind = 'torch'
             self.t_indparams = [torch.as_tensor(a, device=self.dev)
@@ -218,6 +241,25 @@ class Population:
 
     def data_chisq(self, P):
         """(partial, ld, nsplit) holding the data chi-squared of rows of P."""
+        if self.shard == 'data':
+            return self._data_chisq_sharded(P)
+        return self._data_chisq_local(P)
+
+    def _data_chisq_sharded(self, P):
+        """Local-slice sums, then an all-gather of one fp64 per chain and device;
+        the caller adds the `world` rows in rank order (fixed order, identical
+        bits on every device)."""
+        import torch.distributed as dist
+        nb = P.shape[0]
+        part, ld, ns = self._data_chisq_local(P)
+        allsum = self._workspace(('allsum', nb), (self.world, nb))
+        _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, None, 0, 0,
+                  None, None, None, allsum[self.rank].data_ptr(), _lib.stream_ptr())
+        self.launches += 1
+        dist.all_gather_into_tensor(allsum.view(-1), allsum[self.rank], group=self.group)
+        return allsum, nb, self.world
+
+    def _data_chisq_local(self, P):
         nb = P.shape[0]
         st = _lib.stream_ptr()
         if self.wlike:
@@ -337,7 +379,7 @@ class Population:
         _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(), ld, ns,
                   c0, gen, zrow0, c0, c1, st)
         self.launches += 2
-        if self.world > 1:
+        if self.world > 1 and self.shard == 'chains':
             self._exchange(gen)
         if gen < 0:
             _lib.call('mc3b_advance', ctypes.byref(self.S), st)
@@ -375,7 +417,7 @@ class Population:
             return
         if use_graph is None:
             use_graph = self.kind == 'builtin' and not \
-                (self.world > 1 and self.sampler == 'snooker')
+                (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker')
         if not use_graph:
             for g in range(self.gen, self.gen + ngen):
                 self._generation(g)
@@ -459,7 +501,10 @@ class Population:
         return self.M0 + self.thinned_done()*self.nchains
 
     def gather_history(self):
-        """Make Z / log_post / zchain complete on every device (no-op at world=1)."""
+        """Make Z / log_post / zchain complete on every device (no-op at world=1
+        and for data sharding, where the history is replicated)."""
+        if self.shard == 'data':
+            return
         for t in (self.Z, self.log_post, self.zchain):
             gather_history(t, self.M0, self.thinned_done(), self.nchains,
                            self.rank, self.world, self.group)
@@ -468,7 +513,7 @@ class Population:
         """Host copy of the counters (summed over devices)."""
         nacc, oob = self.naccept, self.outbounds
         bc, bx, bg = self.best_chisq, self.best_x, self.best_gen
-        if self.world > 1:
+        if self.world > 1 and self.shard == 'chains':
             import torch.distributed as dist
             lo, n = self.chain0, self.nlocal
             nacc, bg, bx = (sum_owned(t, lo, n, self.group) for t in (nacc, bg, bx))

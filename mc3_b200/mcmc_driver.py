@@ -40,7 +40,7 @@ def eval_model(pop, params, ret='model'):
 
 def calc_bestfit_statistics(bestp, pop):
     """stats.py:855-873."""
-    ndata = pop.ndata
+    ndata = pop.ndata_total
     best_model, opt_chisq = eval_model(pop, bestp, 'both')
     best_log_post = -0.5*opt_chisq
     best_log_prior = ms.log_prior(bestp[pop.ifree], pop.prior, pop.priorlow,
@@ -48,7 +48,7 @@ def calc_bestfit_statistics(bestp, pop):
     best_chisq = -2*(best_log_post - best_log_prior)
     bic = best_chisq + pop.nfree*np.log(ndata)
     red = best_chisq/(ndata - pop.nfree) if ndata > pop.nfree else np.nan
-    data = pop.d_data.cpu().numpy()
+    data = pop.host_data
     return best_chisq, red, bic, best_log_post, best_model, np.std(best_model - data)
 
 
@@ -93,7 +93,8 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
          sampler, wlike, fit_output, grtest, grbreak, grnmin, burnin, thinning,
          fgamma, fepsilon, hsize, kickoff, savefile, resume, log,
          pnames, texnames, seed=None, dtype='f64', device=None, use_graph=None,
-         rank=0, world=1, group=None, reflect=False, return_population=False):
+         rank=0, world=1, group=None, reflect=False, return_population=False,
+         shard='chains'):
     """Reference signature (mcmc_driver.py:18-26; `ncpu` is accepted and
     ignored) plus keyword-only device options."""
     pstep = np.asarray(pstep, float)
@@ -136,7 +137,7 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
         wlike=wlike, fgamma=fgamma, fepsilon=fepsilon, hsize=hsize,
         thinning=thinning, nzchain=nzchain, seed=seed, dtype=dtype,
         device=device, rank=rank, world=world, group=group, reflect=reflect,
-        M0=M0)
+        M0=M0, shard=shard)
 
     if resume:
         _resume(pop, oldrun)

@@ -189,7 +189,7 @@ def sample(data=None, uncert=None, func=None, params=None,
             chisq_factor = float(oldrun['chisq_factor'])
 
     dev_kw = {k: kwargs[k] for k in ('seed', 'dtype', 'device', 'use_graph',
-                                     'reflect', 'rank', 'world', 'group')
+                                     'reflect', 'rank', 'world', 'group', 'shard')
               if k in kwargs}
     output = mcmc(
         data, uncert, func, params, indparams, indparams_dict,
