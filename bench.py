@@ -25,6 +25,7 @@ One JSON line on stdout (rank 0):
 --impl reference prints the same line for the CPU reference arm.
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -287,6 +288,10 @@ def run_ours(args):
     quiet = mc3.Log(verb=-1)
 
     def hub(ngen, seed):
+        with contextlib.redirect_stdout(sys.stderr):      # keep stdout to the one JSON line
+            return _hub(ngen, seed)
+
+    def _hub(ngen, seed):
         return mcmc(host['data'], host['uncert'], model, host['params'], [host['x']], {},
                     host['pmin'], host['pmax'], host['pstep'], host['prior'],
                     host['priorlow'], host['priorup'], nchains, None, nchains*ngen,
