@@ -151,72 +151,140 @@ __global__ void __launch_bounds__(256) k_binrms_main(const double* P, const doub
 // the CTA's tiles in a fixed order; partial[cta, i] leaves at the end.
 constexpr int TT = 8192;
 constexpr int BMAX = 4096;
+constexpr int BWARP = 256;
+constexpr int TNW = 16;            // warps per CTA of the tile kernel          // bin sizes below this: one warp per size; above: one lane per size
 
-__global__ void __launch_bounds__(256) k_binrms_tile(const double* x, int64_t n, int64_t nsmall, int64_t binstep,
-                                                    int halo, int64_t nout, double* partial) {
-    extern __shared__ __align__(128) double sm[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ double wsum[8];
-    double* P = sm;                              // [TT + halo]
-    double* acc = sm + TT + halo;                // [nsmall]
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int64_t i = threadIdx.x; i < nsmall; i += 256) acc[i] = 0.0;
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    __syncthreads();
-    const int64_t ntiles = (n + TT - 1) / TT;
-    uint32_t phase = 0;
+// Skewed shared-memory index: a bin size b makes the lanes of a warp read the
+// prefix with stride b; padding one slot per 16, 256 and 4096 entries spreads
+// every power-of-two stride over the banks.
+__device__ __forceinline__ int pidx(int k) { return k + (k >> 4) + (k >> 8) + (k >> 12); }
+
+__global__ void __launch_bounds__(TNW * 32) k_binrms_tile(const double* __restrict__ x, int64_t n, int64_t nsmall,
+                                                    int64_t binstep, int halo, int64_t nout, double* partial) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ double wsum[TNW], wsq[TNW];
     const int len_full = TT + halo;
-    const int per = (len_full + 255) / 256;      // elements per thread in the scan
+    double* P = sm;                                   // [pidx(len_full) + 1] skewed inclusive prefix
+    double* acc = sm + pidx(len_full) + 1;            // [nsmall] sum of mean^2 per bin size
+    double* invb = acc + nsmall;                      // [nsmall] 1/b
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int step = (int)binstep;
+    for (int i = threadIdx.x; i < (int)nsmall; i += TNW * 32) { acc[i] = 0.0; invb[i] = 1.0 / (double)(1 + i * step); }
+    // first index whose bin size reaches BWARP
+    int nA = (int)nsmall;
+    if (1 + (nsmall - 1) * binstep >= BWARP) nA = (BWARP - 1 + step - 1) / step;
+    const int seg = ((len_full + TNW - 1) / TNW + 31) & ~31;  // points per warp in the scan (multiple of 32)
+    const int64_t ntiles = (n + TT - 1) / TT;
+    __syncthreads();
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t t0 = t * TT;
         const int len = (int)((n - t0) < len_full ? (n - t0) : len_full);
-        if (len == len_full) {
-            if (threadIdx.x == 0) {
-                mbar_expect_tx(&bar, (uint32_t)len_full * 8u);
-                bulk_g2s(P, x + t0, (uint32_t)len_full * 8u, &bar);
+        const int owned = (int)((n - t0) < TT ? (n - t0) : TT);
+        // ---- scan: warp w turns points [w*seg, (w+1)*seg) into a local inclusive prefix
+        {
+            const int k0 = warp * seg;
+            double carry = 0.0, sq = 0.0;
+            for (int c = 0; c < seg; c += 128) {
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = k0 + c + u * 32 + lane;
+                    v[u] = (c + u * 32 < seg && k < len) ? x[t0 + k] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int k = k0 + c + u * 32 + lane;
+                    if (c + u * 32 < seg) {
+                        double r = v[u];
+                        if (k < owned) sq = fma(r, r, sq);
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double up = __shfl_up_sync(0xffffffffu, r, o);
+                            if (lane >= o) r += up;
+                        }
+                        r += carry;
+                        if (k < len) P[pidx(k)] = r;
+                        carry = __shfl_sync(0xffffffffu, r, 31);
+                    }
+                }
             }
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
-        } else {
-            for (int k = threadIdx.x; k < len; k += 256) P[k] = x[t0 + k];
-            __syncthreads();
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) { wsum[warp] = carry; wsq[warp] = sq; }
         }
-        // inclusive prefix of P[0..len) in place
-        const int k0 = threadIdx.x * per, k1 = (k0 + per < len) ? k0 + per : len;
-        double run = 0.0;
-        for (int k = k0; k < k1; k++) { run += P[k]; P[k] = run; }
-        double sc = run;
-        for (int o = 1; o < 32; o <<= 1) {
-            const double v = __shfl_up_sync(0xffffffffu, sc, o);
-            if (lane >= o) sc += v;
+        __syncthreads();
+        {
+            double off = 0.0;
+            for (int w = 0; w < warp; w++) off += wsum[w];
+            if (warp > 0) {
+                const int k0 = warp * seg;
+                for (int k = k0 + lane; k < k0 + seg && k < len; k += 32) P[pidx(k)] += off;
+            }
+            if (threadIdx.x == 0) {                    // bin size 1: sum of squares of the owned points
+                double s2 = 0.0;
+                for (int w = 0; w < TNW; w++) s2 += wsq[w];
+                acc[0] += s2;
+            }
         }
-        if (lane == 31) wsum[warp] = sc;
         __syncthreads();
-        double off = sc - run;
-        for (int k = 0; k < warp; k++) off += wsum[k];
-        for (int k = k0; k < k1; k++) P[k] += off;
-        __syncthreads();
-        // bins: warp w takes bin sizes i = w, w+8, ...
-        const int64_t own_end = (t0 + TT < n) ? t0 + TT : n;
-        for (int64_t i = warp; i < nsmall; i += 8) {
-            const int64_t b = 1 + i * binstep, M = n / b;
-            int64_t j0 = (t0 + b - 1) / b;                          // first bin starting in the tile
-            int64_t j1 = (own_end + b - 1) / b;                     // one past the last such bin
-            if (j1 > M) j1 = M;
-            const double inv = 1.0 / (double)b;
+        const int nl = len;                            // a bin must end inside the data: le <= nl
+        // ---- A: bin sizes 1 < b < BWARP, one warp per size (snake order for balance), lanes over bins
+        for (int r = 0;; r++) {
+            const int slot = (r & 1) ? TNW - 1 - warp : warp;
+            const int i = 1 + r * TNW + slot;
+            if (1 + r * TNW >= nA) break;
+            if (i >= nA) continue;
+            const int b = 1 + i * step;
+            const double inv = invb[i];
+            // first bin starting in the tile: j0 = ceil(t0 / b); local start ls0 = j0*b - t0 in [0, b)
+            int64_t j0 = (int64_t)((double)t0 * inv);
+            int64_t s0 = j0 * b;
+            if (s0 < t0) s0 += b; else if (s0 - b >= t0) s0 -= b;
+            const int ls0 = (int)(s0 - t0);
+            int cnt = 0;
+            if (ls0 < owned) {
+                cnt = (int)((double)(owned - ls0 + b - 1) * inv);
+                while (ls0 + cnt * b < owned) cnt++;
+                while (cnt > 0 && ls0 + (cnt - 1) * b >= owned) cnt--;
+                while (cnt > 0 && ls0 + cnt * b > nl) cnt--;       // incomplete last bin of the series
+            }
             double a = 0.0;
-            for (int64_t j = j0 + lane; j < j1; j += 32) {
-                const int ls = (int)(j * b - t0), le = ls + (int)b;
-                const double sum = P[le - 1] - (ls > 0 ? P[ls - 1] : 0.0);
-                const double m = sum * inv;
-                a = fma(m, m, a);
+            double carry = ls0 > 0 ? P[pidx(ls0 - 1)] : 0.0;
+            for (int base = 0; base < cnt; base += 32) {
+                const int m = base + lane;
+                const bool on = m < cnt;
+                const double e = on ? P[pidx(ls0 + m * b + b - 1)] : 0.0;
+                double prev = __shfl_up_sync(0xffffffffu, e, 1);
+                if (lane == 0) prev = carry;
+                if (on) { const double mean = (e - prev) * inv; a = fma(mean, mean, a); }
+                carry = __shfl_sync(0xffffffffu, e, 31);
             }
             for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
             if (lane == 0) acc[i] += a;
         }
-        __syncthreads();                         // tile buffer free again
+        // ---- B: bin sizes >= BWARP, one lane per size (few bins each)
+        for (int g = warp; nA + g * 32 < (int)nsmall; g += TNW) {
+            const int i = nA + g * 32 + lane;
+            if (i < (int)nsmall) {
+                const int b = 1 + i * step;
+                const double inv = invb[i];
+                int64_t j0 = (int64_t)((double)t0 * inv);
+                int64_t s0 = j0 * b;
+                if (s0 < t0) s0 += b; else if (s0 - b >= t0) s0 -= b;
+                int ls = (int)(s0 - t0);
+                double a = 0.0;
+                double prev = ls > 0 ? P[pidx(ls - 1)] : 0.0;
+                while (ls < owned && ls + b <= nl) {
+                    const double e = P[pidx(ls + b - 1)];
+                    const double mean = (e - prev) * inv;
+                    a = fma(mean, mean, a);
+                    prev = e;
+                    ls += b;
+                }
+                acc[i] += a;
+            }
+        }
+        __syncthreads();                               // tile buffer free again
     }
-    for (int64_t i = threadIdx.x; i < nsmall; i += 256) partial[(int64_t)blockIdx.x * nout + i] = acc[i];
+    for (int i = threadIdx.x; i < (int)nsmall; i += TNW * 32) partial[(int64_t)blockIdx.x * nout + i] = acc[i];
 }
 
 // One thread per bin size: rms, asymptotic errors, Gaussian extrapolation, and
@@ -342,17 +410,6 @@ __global__ void __launch_bounds__(256) k_binarray_big(const double* d, const dou
 // coalesced 8-byte loads (4 independent loads in flight per lane at binsize 100,
 // 64 resident warps per SM keep ~64 KB in flight), fixed-order lane tree.  Short
 // bins (< 32 points) take one thread per bin.
-// 1/v for the weights: single-precision seed + two Newton steps in fp64 (error
-// < 2 ulp, no slow-path branches); values outside the float range take the
-// exact division.
-__device__ __forceinline__ double fast_rcp(double v) {
-    if (!(v > 1e-30 && v < 1e30)) return 1.0 / v;
-    double x = (double)__frcp_rn((float)v);
-    x = x * fma(-v, x, 2.0);
-    x = x * fma(-v, x, 2.0);
-    return fma(x, fma(-v, x, 1.0), x);
-}
-
 template <bool W, int NB>
 __global__ void __launch_bounds__(256) k_binarray_direct(const double* __restrict__ d, const double* __restrict__ u,
                                                         int64_t nbins, int64_t binsize, double* bd, double* bs) {
@@ -384,7 +441,7 @@ __global__ void __launch_bounds__(256) k_binarray_direct(const double* __restric
                 for (int j = 0; j < 8; j++) {
                     if (W) {
                         const int64_t k = base + lane + 32 * j;
-                        const double ww = (k < binsize) ? fast_rcp(sg[q][j] * sg[q][j]) : 0.0;
+                        const double ww = (k < binsize) ? 1.0 / (sg[q][j] * sg[q][j]) : 0.0;
                         w[q] += ww;
                         a[q] = fma(v[q][j], ww, a[q]);
                     } else {
@@ -434,6 +491,11 @@ __global__ void __launch_bounds__(256) k_binarray_short(const double* __restrict
     }
 }
 
+static size_t tile_smem_bytes(int halo, int64_t nsmall) {
+    const int lf = TT + halo;
+    return (size_t)((lf + (lf >> 4) + (lf >> 8) + (lf >> 12)) + 1 + 2 * nsmall) * 8;
+}
+
 struct RmsLayout { int64_t nblk, nout, nsmall; int ys, rows, tile_ctas, halo; bool use_tile, need_prefix;
                    int64_t oP, oTot, oT2, oDev, oPart, oIg, oLohi, oStat, oLead, words; };
 
@@ -454,7 +516,7 @@ RmsLayout rms_layout(int64_t n, int64_t maxbins, int64_t binstep, bool allow_til
     L.halo = (int)(((bsmall - 1) + 1) & ~1LL);                 // even: whole 16-byte units
     int sms = mc3b_sm_count();
     if (sms <= 0) sms = 148;
-    const size_t tile_smem = (size_t)(TT + L.halo + L.nsmall) * 8;
+    const size_t tile_smem = tile_smem_bytes(L.halo, L.nsmall);
     L.tile_ctas = sms * (tile_smem <= 100 * 1024 ? 2 : 1);
     const int64_t ntiles = ceil_div64(n, TT);
     if (L.tile_ctas > ntiles) L.tile_ctas = (int)ntiles;
@@ -507,9 +569,9 @@ extern "C" int mc3b_binrms(const double* data, int64_t n, int64_t maxbins, int64
     MC3B_CHECK_LAUNCH("k_std");
     MC3B_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)L.rows * L.nout, st));
     if (L.nsmall > 0) {
-        const size_t smem = (size_t)(TT + L.halo + L.nsmall) * 8;
+        const size_t smem = tile_smem_bytes(L.halo, L.nsmall);
         MC3B_CUDA(cudaFuncSetAttribute(k_binrms_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_binrms_tile<<<(unsigned)L.tile_ctas, 256, smem, st>>>(data, n, L.nsmall, binstep, L.halo, L.nout, part);
+        k_binrms_tile<<<(unsigned)L.tile_ctas, TNW * 32, smem, st>>>(data, n, L.nsmall, binstep, L.halo, L.nout, part);
         MC3B_CHECK_LAUNCH("k_binrms_tile");
     }
     if (L.need_prefix) {
