@@ -267,9 +267,10 @@ def run_ours(args):
         # FP64-pipe instructions per (chain, point) of the sinusoid kernel, read off
         # the SASS (profiles/r1_model_chisq.md): 14 sine + 2 argument/line + 1 model
         # + 3 residual/square = 20; each occupies the pipe like one FMA (2 flops).
-        pipe_instr = 20.0
+        pipe_instr = 9.0 if getattr(pop, 'grid', False) else 20.0   # uniform-grid recurrence: 4+2+3
         roof = {'bound': 'fp64' if args.dtype == 'f64' else 'fp32',
-                'kernel': 'k_model_chisq<SineModel>',
+                'kernel': 'k_model_chisq<SineGridModel>' if getattr(pop, 'grid', False) else 'k_model_chisq<SineModel>',
+                'fp64_pipe_instr_per_chain_point': pipe_instr,
                 'achieved': achieved/1e12, 'peak': best/1e12, 'unit': 'TFLOP/s',
                 'frac': achieved/best, 'traffic': prof.get('dram_bytes_per_launch'),
                 'traffic_source': prof.get('source'),

@@ -33,7 +33,10 @@ extern "C" {
 enum { MC3B_OK = 0, MC3B_ERR_ARG = 1, MC3B_ERR_CUDA = 2 };
 enum { MC3B_F64 = 0, MC3B_F32 = 1 };
 enum { MC3B_MODEL_POLYNOMIAL = 0, MC3B_MODEL_SINUSOID = 1,
-       MC3B_MODEL_GAUSSIAN = 2, MC3B_MODEL_BOX = 3 };
+       MC3B_MODEL_GAUSSIAN = 2, MC3B_MODEL_BOX = 3,
+       /* sinusoid on a UNIFORM abscissa grid (caller's assertion): same values to
+        * ~1e-14, the sine advances by a rotation recurrence re-anchored per tile */
+       MC3B_MODEL_SINUSOID_GRID = 4 };
 enum { MC3B_MRW = 0, MC3B_DEMC = 1, MC3B_SNOOKER = 2 };
 
 #define MC3B_MAX_PARS 32            /* parameters per model vector          */

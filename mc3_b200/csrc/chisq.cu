@@ -17,6 +17,7 @@
 //
 // Bound: FP64 (or FP32) pipe -- nchains*F flops per 24 bytes of data.
 #include <stdlib.h>
+#include <type_traits>
 #include "models.cuh"
 
 namespace {
@@ -55,7 +56,12 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
     for (int k = 0; k < CPT; k++) {
         int64_t c = cbase + (int64_t)k * LC;
         if (c >= a.nchains) c = a.nchains - 1;      // idle lanes shadow the last chain
-        mdl[k].load(a.params + c * a.ldp);
+        if constexpr (M::TILE_STATE) {
+            const double dx = ((double)a.x[a.n - 1] - (double)a.x[0]) / (double)(a.n - 1);
+            mdl[k].load(a.params + c * a.ldp, dx);
+        } else {
+            mdl[k].load(a.params + c * a.ldp);
+        }
     }
     double acc[CPT];
 #pragma unroll
@@ -87,6 +93,11 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
             mbar_wait(&bar[s], (uint32_t)((it / STAGES) & 1));
             constexpr int U = 4;                // points in flight per lane
             static_assert(TILE % (U * LP) == 0, "tile must hold whole groups");
+            if constexpr (M::TILE_STATE) {
+                static_assert(LP == 1, "stateful models walk a tile in order: one chain per lane");
+#pragma unroll
+                for (int k = 0; k < CPT; k++) mdl[k].begin_tile((double)sx[s][0], TILE);
+            }
             T tacc[CPT], uacc[CPT][U];          // one accumulator per point slot: no serial tail
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
@@ -223,6 +234,17 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
     a.use_tma = ((((uintptr_t)x | (uintptr_t)d | (uintptr_t)w) & 15) == 0) ? 1 : 0;
     Shape sh = plan_shape(nchains, n, dtype, mc3b_sm_count());
     MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
+    if (model_id == MC3B_MODEL_SINUSOID_GRID) {
+        if constexpr (std::is_same<T, double>::value) {
+            if (sh.lc == 32 && sh.cpt == 1 && a.use_tma && n >= 2) {
+                dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
+                k_model_chisq<SineGridModel, double, 32, 1><<<grid, block, 0, st>>>(a);
+                MC3B_CHECK_LAUNCH("k_model_chisq<grid>");
+                return MC3B_OK;
+            }
+        }
+        model_id = MC3B_MODEL_SINUSOID;             // small populations, fp32, unaligned: plain model
+    }
     MC3B_DISPATCH_MODEL(T, model_id, nmodel, return (launch_model_chisq<M, T>(sh, a, nsplit, st)));
     return MC3B_OK;
 }
@@ -323,6 +345,7 @@ extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, i
 
 extern "C" int mc3b_model_eval(int model_id, const double* params, int64_t ldp, int64_t nchains, int nmodel,
                                const double* x, int64_t n, double* out, void* stream) {
+    if (model_id == MC3B_MODEL_SINUSOID_GRID) model_id = MC3B_MODEL_SINUSOID;
     MC3B_CHECK_ARG(params && x && out && nchains > 0 && n > 0, "bad arguments");
     MC3B_CHECK_ARG(mc3b_model_nparams(model_id, nmodel) == nmodel, "model %d does not take %d parameters",
                    model_id, nmodel);

@@ -332,6 +332,7 @@ extern "C" int mc3b_dwt_chisq(int model_id, const double* params, int64_t ldp, i
         return dwt_run<SRC_GIVEN, M>(sc, kbits, params, ldp, nchains, npars, x, model, ldm, data, n, ws, chisq, st);
     }
     MC3B_CHECK_ARG(x != nullptr, "built-in model needs x");
+    if (model_id == MC3B_MODEL_SINUSOID_GRID) model_id = MC3B_MODEL_SINUSOID;
     MC3B_CHECK_ARG(mc3b_model_nparams(model_id, nmodel) == nmodel && nmodel <= npars - 3,
                    "model %d does not take %d parameters", model_id, nmodel);
     MC3B_DISPATCH_MODEL(double, model_id, nmodel,

@@ -43,6 +43,31 @@ __device__ __forceinline__ double fast_sin_core(double a, double magic) {
     const double v = fma(r * s, p, r);
     return __hiloint2double(__double2hiint(v) ^ (__double2loint(t) << 31), __double2loint(v));
 }
+// sin and cos of the same argument (shared reduction); cos(r) = 1 - s/2 + s^2 Q(s),
+// Q of degree 6 (near-minimax, max error 7e-17 on [-pi/2, pi/2]).
+__device__ __constant__ double kCosC[8] = {
+    4.6464359591124806e-14, -1.1466252259718479e-11, 2.0876681558867395e-09, -2.7557318573366175e-07,
+    2.480158729891355e-05, -0.0013888888888884767, 0.04166666666666666, 0.0};
+
+__device__ __forceinline__ void fast_sincos_core(double a, double& sn, double& cs) {
+    const double t = fma(a, kSinC[0], MC3B_SIN_MAGIC);
+    const double q = t - MC3B_SIN_MAGIC;
+    double r = fma(q, kSinC[1], a);
+    r = fma(q, kSinC[2], r);
+    const double s = r * r;
+    double p = fma(s, kSinC[3], kSinC[4]);
+    double h = fma(s, kCosC[0], kCosC[1]);
+#pragma unroll
+    for (int i = 5; i <= 10; i++) p = fma(p, s, kSinC[i]);
+#pragma unroll
+    for (int i = 2; i <= 6; i++) h = fma(h, s, kCosC[i]);
+    const double v = fma(r * s, p, r);
+    const double w = fma(s * s, h, fma(s, -0.5, 1.0));
+    const int flip = __double2loint(t) << 31;
+    sn = __hiloint2double(__double2hiint(v) ^ flip, __double2loint(v));
+    cs = __hiloint2double(__double2hiint(w) ^ flip, __double2loint(w));
+}
+
 // The fast path is valid for |a| < 1e9 (finite); callers check with this.
 __device__ __forceinline__ int sin_arg_key(double a) { return __double2hiint(a) & 0x7fffffff; }
 #define MC3B_SIN_KEY_LIMIT 0x41cdcd65
@@ -71,6 +96,7 @@ template <> struct mathx<float> {
 //   eval_safe(x) always valid (slow path); clear() resets the flag
 template <typename T, int NP> struct PolyModel {
     static constexpr bool GUARD = false;
+    static constexpr bool TILE_STATE = false;
     __device__ __forceinline__ bool flagged() const { return false; }
     __device__ __forceinline__ void clear() {}
     __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
@@ -90,6 +116,7 @@ template <typename T, int NP> struct PolyModel {
 // y = p0 sin(2 pi x / p1 + p2) + p3 + p4 x        (BASELINE config 2)
 template <typename T> struct SineModel {
     static constexpr bool GUARD = false;
+    static constexpr bool TILE_STATE = false;
     __device__ __forceinline__ bool flagged() const { return false; }
     __device__ __forceinline__ void clear() {}
     T a, k, ph, c, s;
@@ -107,6 +134,7 @@ template <typename T> struct SineModel {
 // checked once per tile by the kernel, which then redoes the tile with eval_safe.
 template <> struct SineModel<double> {
     static constexpr bool GUARD = true;
+    static constexpr bool TILE_STATE = false;
     double a, k, ph, c, s, magic;
     int keymax;
 #ifdef MC3B_SIN_REGCONST
@@ -170,9 +198,62 @@ template <> struct SineModel<double> {
     }
 };
 
+// Sinusoid on a uniform grid x_i = x_0 + i dx (fp64, one chain per lane walking
+// the points of a tile in order, four at a time).  sin(k x_i + ph) is not
+// evaluated per point: four interleaved sequences (points i = 0,1,2,3 mod 4)
+// each advance by the rotation (s, c) <- (s cd4 + c sd4, c cd4 - s sd4) with
+// cd4 = cos(4 k dx), sd4 = sin(4 k dx); every tile restarts them from directly
+// evaluated values (fast_sincos_core at the tile's first point, three one-step
+// rotations), so rounding accumulates over 64 steps only (<~1e-14 absolute).
+// Per point: 4 (rotation) + 2 (model) + 3 (residual, square) FP64 instructions
+// instead of 20.
+struct SineGridModel {
+    static constexpr bool GUARD = true;
+    static constexpr bool TILE_STATE = true;
+    double a, k, ph, c0, sl, cd1, sd1, cd4, sd4, dth;
+    double s[4], c[4];
+    int keymax;
+    __device__ __forceinline__ void load(const double* p, double dx) {
+        a = p[0]; k = 6.283185307179586476925287 / p[1]; ph = p[2]; c0 = p[3]; sl = p[4];
+        dth = k * dx;
+        sincos(dth, &sd1, &cd1);
+        sincos(4.0 * dth, &sd4, &cd4);
+        keymax = 0;
+    }
+    // x0: first point this lane visits in the tile; npts: points of the tile
+    __device__ __forceinline__ void begin_tile(double x0, int npts) {
+        const double th = fma(x0, k, ph);
+        keymax = max(keymax, max(sin_arg_key(th), sin_arg_key(fma((double)npts, dth, th))));
+        fast_sincos_core(th, s[0], c[0]);
+#pragma unroll
+        for (int u = 1; u < 4; u++) {
+            s[u] = fma(c[u - 1], sd1, s[u - 1] * cd1);
+            c[u] = fma(-s[u - 1], sd1, c[u - 1] * cd1);
+        }
+    }
+    template <int U> __device__ __forceinline__ void evalN(const double (&x)[U], double (&y)[U]) {
+        static_assert(U == 4, "four interleaved sequences");
+#pragma unroll
+        for (int u = 0; u < U; u++) y[u] = fma(a, s[u], fma(sl, x[u], c0));
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const double sn = fma(c[u], sd4, s[u] * cd4);
+            const double cn = fma(-s[u], sd4, c[u] * cd4);
+            s[u] = sn; c[u] = cn;
+        }
+    }
+    __device__ __forceinline__ double eval(double x) const { return eval_safe(x); }
+    __device__ __forceinline__ bool flagged() const { return keymax >= MC3B_SIN_KEY_LIMIT; }
+    __device__ __forceinline__ void clear() { keymax = 0; }
+    __device__ __forceinline__ double eval_safe(double x) const {
+        return fma(a, sin(fma(x, k, ph)), fma(sl, x, c0));
+    }
+};
+
 // y = p0 exp(-0.5 ((x - p1)/p2)^2) + p3           (Gaussian line)
 template <typename T> struct GaussModel {
     static constexpr bool GUARD = false;
+    static constexpr bool TILE_STATE = false;
     __device__ __forceinline__ bool flagged() const { return false; }
     __device__ __forceinline__ void clear() {}
     __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
@@ -189,6 +270,7 @@ template <typename T> struct GaussModel {
 // y = p3 - p0 [ |x - p1| < p2/2 ]                 (transit-like box, config 3)
 template <typename T> struct BoxModel {
     static constexpr bool GUARD = false;
+    static constexpr bool TILE_STATE = false;
     __device__ __forceinline__ bool flagged() const { return false; }
     __device__ __forceinline__ void clear() {}
     __device__ __forceinline__ T eval_safe(T x) const { return eval(x); }
@@ -238,6 +320,7 @@ static inline int mc3b_model_nparams(int model_id, int nmodel) {
     switch (model_id) {
     case MC3B_MODEL_POLYNOMIAL: return nmodel;
     case MC3B_MODEL_SINUSOID: return 5;
+    case MC3B_MODEL_SINUSOID_GRID: return 5;
     case MC3B_MODEL_GAUSSIAN: return 4;
     case MC3B_MODEL_BOX: return 4;
     }

@@ -28,12 +28,13 @@ HBM layout (all fp64 unless noted; row-major):
     partial   [nsplit, nchains]  per-split chi-squared partial sums
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
 
 from . import _lib
-from .models import BuiltinModel, TorchModel
+from .models import BuiltinModel, TorchModel, SINUSOID, SINUSOID_GRID
 from .parallel import chain_slice, allgather_rows, gather_history, sum_owned
 
 _DT = {'f64': _lib.F64, 'f32': _lib.F32, np.float64: _lib.F64, np.float32: _lib.F32}
@@ -120,6 +121,16 @@ class Population:
             x = x[lo:hi]
             self.d_x = torch.from_numpy(x).to(self.dev)
             self.d_invsig = 1.0/self.d_uncert
+            # A sinusoid on a uniform abscissa grid takes the rotation-recurrence
+            # kernel (models.cuh SineGridModel); MC3B_NO_GRID=1 forces the plain one.
+            self.chisq_model_id = func.model_id
+            self.grid = False
+            if func.model_id == SINUSOID and self.dtype == _lib.F64 and x.size >= 8 \
+                    and not os.environ.get('MC3B_NO_GRID'):
+                ideal = x[0] + np.arange(x.size)*((x[-1] - x[0])/(x.size - 1))
+                if x[-1] != x[0] and np.max(np.abs(x - ideal)) <= 8*np.finfo(float).eps*np.max(np.abs(x)):
+                    self.chisq_model_id = SINUSOID_GRID
+                    self.grid = True
             if self.dtype == _lib.F32:
                 self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
                                                 (self.d_x, self.d_data, self.d_invsig))
@@ -282,7 +293,7 @@ class Population:
         if self.kind == 'builtin':
             ns = self._plan(nb)
             part = self._workspace(('part', nb), (ns, nb))
-            _lib.call('mc3b_model_chisq', self.func.model_id, self.dtype,
+            _lib.call('mc3b_model_chisq', self.chisq_model_id, self.dtype,
                       P.data_ptr(), _lib.ld(P), nb, self.nmodel,
                       self.k_x.data_ptr(), self.k_d.data_ptr(),
                       self.k_w.data_ptr(), self.ndata, part.data_ptr(), nb, ns, st)

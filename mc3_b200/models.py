@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 
-POLYNOMIAL, SINUSOID, GAUSSIAN, BOX = 0, 1, 2, 3
+POLYNOMIAL, SINUSOID, GAUSSIAN, BOX, SINUSOID_GRID = 0, 1, 2, 3, 4
 
 
 class BuiltinModel:

@@ -414,3 +414,44 @@ def test_bin_array_sizes(mc3, bs):
     ww, ws = ok.bin_array(d, bs, u)
     np.testing.assert_allclose(gw, ww, rtol=R64)
     np.testing.assert_allclose(gs, ws, rtol=R64)
+
+
+def test_sinusoid_grid_recurrence_accuracy(mc3):
+    """Uniform-grid sinusoid kernel (rotation recurrence re-anchored per tile):
+    with data = 0 and unit weights chi-squared is sum(model^2); it must agree
+    with numpy to ~1e-13 for benign and for stiff phases (many radians per
+    step, long series), and match the plain kernel's chi-squared at 1e-10."""
+    import torch
+    from mc3_b200 import _lib
+    rs = np.random.RandomState(17)
+    for n, span, nch in ((100000, 10.0, 256), (1 << 20, 5000.0, 128), (4099, 1.0, 200)):
+        x = np.linspace(-0.3*span, 0.7*span, n)
+        P = np.column_stack([rs.uniform(0.5, 2, nch), rs.uniform(0.01, 3.0, nch),
+                             rs.uniform(-3, 3, nch), rs.uniform(-1, 1, nch),
+                             rs.uniform(-0.1, 0.1, nch)])
+        data, unc = np.zeros(n), np.ones(n)
+        dev = torch.device('cuda')
+        dP, dx, dd, dw = (torch.from_numpy(a).to(dev) for a in (P, x, data, unc))
+        outs = {}
+        for mid in (_lib.load() and 1, 4):
+            ns = ctypes.c_int(0)
+            _lib.call('mc3b_model_chisq_plan', nch, n, _lib.F64, ctypes.byref(ns))
+            part = torch.empty((ns.value, nch), dtype=torch.float64, device=dev)
+            _lib.call('mc3b_model_chisq', mid, _lib.F64, dP.data_ptr(), 5, nch, 5,
+                      dx.data_ptr(), dd.data_ptr(), dw.data_ptr(), n, part.data_ptr(),
+                      nch, ns.value, _lib.stream_ptr())
+            outs[mid] = part.sum(dim=0).cpu().numpy()
+        want = np.array([np.sum(om.sinusoid(p, x)**2) for p in P[:24]])
+        np.testing.assert_allclose(outs[4][:24], want, rtol=5e-13)
+        np.testing.assert_allclose(outs[4], outs[1], rtol=1e-11)
+
+
+def test_population_picks_grid_kernel_only_for_uniform_x(mc3):
+    from mc3_b200.engine import Population
+    p = pb.mcmc_case('sine')
+    kw = dict(pstep=p['pstep'], pmin=p['pmin'], pmax=p['pmax'], nchains=128, sampler='demc')
+    pop = Population(p['data'], p['uncert'], mc3.models.sinusoid, p['params'], [p['x']], {}, **kw)
+    assert pop.grid
+    xj = p['x'] + 1e-9*np.sin(np.arange(p['x'].size))
+    pop2 = Population(p['data'], p['uncert'], mc3.models.sinusoid, p['params'], [xj], {}, **kw)
+    assert not pop2.grid
