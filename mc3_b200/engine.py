@@ -37,6 +37,26 @@ from . import _lib
 from .models import BuiltinModel, TorchModel, SINUSOID, SINUSOID_GRID
 from .parallel import chain_slice, allgather_rows, gather_history, sum_owned
 
+_PINNED = {}
+
+
+def to_host(t):
+    """Device tensor -> new numpy array through a cached pinned staging buffer
+    (pageable D2H of the 10-100 MB history costs several times the PCIe time)."""
+    if t.numel() == 0 or t.numel()*t.element_size() < (1 << 20):
+        return t.cpu().numpy()
+    t = t.contiguous()
+    key = t.dtype
+    buf = _PINNED.get(key)
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+        _PINNED[key] = buf
+    view = buf[:t.numel()].view(t.shape)
+    view.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return view.numpy().copy()
+
+
 _DT = {'f64': _lib.F64, 'f32': _lib.F32, np.float64: _lib.F64, np.float32: _lib.F32}
 
 
@@ -568,8 +588,8 @@ class Population:
                   self.log_post[lo:hi].data_ptr(), None, chisq.data_ptr(),
                   _lib.stream_ptr())
         self.launches += 1
-        return (self.Z[lo:hi].cpu().numpy(), self.zchain[lo:hi].cpu().numpy().astype(int),
-                self.log_post[lo:hi].cpu().numpy(), chisq.cpu().numpy())
+        return (to_host(self.Z[lo:hi]), to_host(self.zchain[lo:hi]).astype(int),
+                to_host(self.log_post[lo:hi]), to_host(chisq))
 
     def sample_statistics(self, zburn, quantile=0.683):
         """median, mean, std and central-quantile bounds of the burned posterior,
