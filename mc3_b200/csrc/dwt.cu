@@ -132,6 +132,103 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_pass(PassArgs a) {
     }
 }
 
+// ---- register stage: 4 levels per pass without the shared-memory round trips --
+// A warp takes blocks of 512 consecutive inputs of its chain (read modulo n).
+// The block is loaded/evaluated coalesced, transposed once through a padded
+// shared-memory row so that lane l owns inputs [16 l, 16 l + 16), and the four
+// levels then run in registers: each level needs two values of the next lane
+// (shuffle) and halves the lane's values (16 -> 8 -> 4 -> 2 -> 1).  Lane 31 has
+// no right neighbour, so the last 2 of the 32 level-4 outputs are not valid:
+// blocks advance by 480 inputs (30 outputs) and an output is counted by the
+// block that owns its first input.  Shared-memory traffic drops from ~64 to 16
+// bytes per input; the FP64 pipe becomes the limiter.
+constexpr int RB = 512;             // inputs per block
+constexpr int RADV = 480;           // block advance (30 lanes x 16)
+
+struct RegArgs {
+    const double* params; int64_t ldp; int64_t nchains;
+    const double* x; const double* data;
+    const double* rows; int64_t ldr;
+    int64_t n_in;
+    int lev0;
+    int64_t nblocks; int blocks_per_span;
+    double* out; int64_t ldo;
+    double* sums;
+};
+
+template <int SRC, class M>
+__global__ void __launch_bounds__(CH * 32) k_dwt_reg(RegArgs a) {
+    __shared__ double tr[CH][RB + RB / 16];          // padded transpose rows (stride 17)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t c = (int64_t)blockIdx.x * CH + warp;
+    const bool live = c < a.nchains;
+    if (!live) c = a.nchains - 1;
+    M mdl;
+    if (SRC == SRC_MODEL) mdl.load(a.params + c * a.ldp);
+    const double* row = (SRC == SRC_MODEL) ? nullptr : a.rows + c * a.ldr;
+    const double c0 = kC[0], c1 = kC[1], c2 = kC[2], c3 = kC[3];
+    const int64_t mask = a.n_in - 1;
+    double* T_ = tr[warp];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t b_begin = (int64_t)blockIdx.y * a.blocks_per_span;
+    int64_t b_end = b_begin + a.blocks_per_span;
+    if (b_end > a.nblocks) b_end = a.nblocks;
+    for (int64_t b = b_begin; b < b_end; b++) {
+        const int64_t g0 = b * RADV;
+        // coalesced load (+ model, residual), transposed through shared memory
+#pragma unroll 4
+        for (int i = 0; i < 16; i++) {
+            const int idx = i * 32 + lane;
+            const int64_t g = (g0 + idx) & mask;
+            double r;
+            if (SRC == SRC_MODEL) r = a.data[g] - mdl.eval_safe(a.x[g]);
+            else if (SRC == SRC_GIVEN) r = a.data[g] - row[g];
+            else r = row[g];
+            T_[idx + (idx >> 4)] = r;
+        }
+        __syncwarp();
+        double v[18];
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = T_[lane * 17 + k];
+        __syncwarp();
+        // four levels in registers
+        int cnt = 16;                                  // values this lane holds
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            v[cnt] = __shfl_down_sync(0xffffffffu, v[0], 1);
+            v[cnt + 1] = __shfl_down_sync(0xffffffffu, v[1], 1);
+            const int half = cnt >> 1;
+            // ownership: output o = lane*half + j of this block at this level
+            const int64_t lev_pos0 = (g0 >> (l + 1)) + (int64_t)lane * half;
+            const int64_t lev_n = a.n_in >> (l + 1);
+            const int own_limit = RADV >> (l + 1);
+            double s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j < half) {
+                    const double a0 = v[2 * j], a1 = v[2 * j + 1], a2 = v[2 * j + 2], a3 = v[2 * j + 3];
+                    const double sm = fma(c3, a3, fma(c2, a2, fma(c1, a1, c0 * a0)));
+                    const double d = fma(-c0, a3, fma(c1, a2, fma(-c2, a1, c3 * a0)));
+                    const bool own = (lane * half + j < own_limit) && (lev_pos0 + j < lev_n);
+                    s2 = fma(d, own ? d : 0.0, s2);
+                    v[j] = sm;                         // j <= 2j: safe in-place
+                }
+            }
+            acc[l] += s2;
+            cnt = half;
+        }
+        // v[0] = level-4 smooth output of lane (valid for lanes < 30)
+        const int64_t o = (g0 >> 4) + lane;
+        if (live && lane < 30 && o < (a.n_in >> 4)) a.out[c * a.ldo + o] = v[0];
+    }
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        double t = acc[l];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && live) a.sums[(c * MAXLEV + (a.lev0 + l)) * MAXSPAN + blockIdx.y] = t;
+    }
+}
+
 struct LastArgs {
     const double* params; int64_t ldp; int npars; int64_t nchains;
     const double* x; const double* data;
@@ -235,7 +332,8 @@ __global__ void k_d4_inv(const double* s, const double* d, double* out, int64_t 
 int ilog2(int64_t n) { int k = 0; while ((1LL << k) < n) k++; return k; }
 
 struct Schedule {
-    int npass; int L[8]; int64_t nin[8]; int spans[8]; int tps[8];
+    int npass; int L[8]; int64_t nin[8]; int spans[8]; int tps[8]; int kind[8];   // kind 1 = register stage
+    int64_t nblocks[8];
     int n0, lev0;
 };
 
@@ -243,10 +341,21 @@ Schedule make_schedule(int64_t n) {
     Schedule s; s.npass = 0; s.lev0 = 0;
     int64_t cur = n;
     while (cur > LASTMAX) {
+        if (cur >= 16 * LASTMAX) {                   // register stage: 4 levels, blocks of 512 advancing by 480
+            const int64_t nb = ceil_div64(cur, RADV);
+            const int spans = (int)(nb < MAXSPAN ? nb : MAXSPAN);
+            s.kind[s.npass] = 1; s.L[s.npass] = 4; s.nin[s.npass] = cur; s.spans[s.npass] = spans;
+            s.nblocks[s.npass] = nb; s.tps[s.npass] = (int)ceil_div64(nb, spans);
+            s.npass++;
+            s.lev0 += 4;
+            cur >>= 4;
+            continue;
+        }
         int L = ilog2(cur / LASTMAX);
-        if (L > LMAX) L = LMAX - 1;                  // 5 then 6 for 2^20
+        if (L > LMAX) L = LMAX - 1;
         const int64_t tiles = cur / T;
         int spans = (int)(tiles < MAXSPAN ? tiles : MAXSPAN);
+        s.kind[s.npass] = 0; s.nblocks[s.npass] = 0;
         s.L[s.npass] = L; s.nin[s.npass] = cur; s.spans[s.npass] = spans; s.tps[s.npass] = (int)(tiles / spans);
         s.npass++;
         s.lev0 += L;
@@ -285,6 +394,23 @@ static int dwt_run(const Schedule& sc, int kbits, const double* params, int64_t 
     const double* cur_rows = model; int64_t cur_ld = ldm;
     int lev0 = 0;
     for (int p = 0; p < sc.npass; p++) {
+        if (sc.kind[p] == 1) {
+            RegArgs r;
+            r.params = params; r.ldp = ldp; r.nchains = nchains; r.x = x; r.data = data;
+            r.rows = cur_rows; r.ldr = cur_ld; r.n_in = sc.nin[p]; r.lev0 = lev0;
+            r.nblocks = sc.nblocks[p]; r.blocks_per_span = sc.tps[p];
+            r.out = (p % 2 == 0) ? ping : pong; r.ldo = sc.nin[p] >> 4; r.sums = sums;
+            // spans actually needed with whole blocks per span
+            const int spans = (int)ceil_div64(sc.nblocks[p], sc.tps[p]);
+            dim3 grid(groups, (unsigned)spans);
+            if (p == 0) k_dwt_reg<SRC, M><<<grid, CH * 32, 0, st>>>(r);
+            else k_dwt_reg<SRC_ARRAY, BoxModel<double>><<<grid, CH * 32, 0, st>>>(r);
+            MC3B_CHECK_LAUNCH("k_dwt_reg");
+            for (int l = 0; l < 4; l++) la.spans_of_level[lev0 + l] = spans;
+            lev0 += 4;
+            cur_rows = r.out; cur_ld = r.ldo;
+            continue;
+        }
         PassArgs a;
         a.params = params; a.ldp = ldp; a.nchains = nchains; a.x = x; a.data = data;
         a.rows = cur_rows; a.ldr = cur_ld; a.n_in = sc.nin[p]; a.L = sc.L[p]; a.lev0 = lev0;

@@ -283,7 +283,7 @@ def test_builtin_models_evaluate_on_gpu(mc3):
 
 
 # ---- wavelet likelihood with built-in model, batched ------------------------
-@pytest.mark.parametrize('n', [64, 512, 2048, 65536])
+@pytest.mark.parametrize('n', [64, 512, 2048, 8192, 65536, 1 << 17, 1 << 20])
 def test_dwt_chisq_builtin_batched(mc3, n):
     from mc3_b200 import _lib
     dev = torch.device('cuda')
