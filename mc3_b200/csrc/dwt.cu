@@ -18,6 +18,7 @@
 //
 // For n = 2^20: pass(L=5) -> 2^15, pass(L=6) -> 512, last.  Bound: FP64 pipe
 // (about 8 FMA-class instructions per input point over all levels + model).
+#include <type_traits>
 #include "models.cuh"
 
 namespace {
@@ -173,17 +174,28 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg(RegArgs a) {
     const int64_t b_begin = (int64_t)blockIdx.y * a.blocks_per_span;
     int64_t b_end = b_begin + a.blocks_per_span;
     if (b_end > a.nblocks) b_end = a.nblocks;
-    for (int64_t b = b_begin; b < b_end; b++) {
+    // One block.  INTERIOR: the 512 inputs do not wrap and every output the block
+    // owns exists (no index masking, ownership is just lane < 30).
+    auto do_block = [&](int64_t b, auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
         const int64_t g0 = b * RADV;
-        // coalesced load (+ model, residual), transposed through shared memory
+        const double* px = (SRC == SRC_MODEL) ? a.x + g0 : nullptr;
+        const double* pd = (SRC == SRC_ARRAY) ? nullptr : a.data + g0;
+        const double* pr = (SRC == SRC_MODEL) ? nullptr : row + g0;
 #pragma unroll 4
         for (int i = 0; i < 16; i++) {
             const int idx = i * 32 + lane;
-            const int64_t g = (g0 + idx) & mask;
             double r;
-            if (SRC == SRC_MODEL) r = a.data[g] - mdl.eval_safe(a.x[g]);
-            else if (SRC == SRC_GIVEN) r = a.data[g] - row[g];
-            else r = row[g];
+            if (INTERIOR) {
+                if (SRC == SRC_MODEL) r = pd[idx] - mdl.eval_safe(px[idx]);
+                else if (SRC == SRC_GIVEN) r = pd[idx] - pr[idx];
+                else r = pr[idx];
+            } else {
+                const int64_t g = (g0 + idx) & mask;
+                if (SRC == SRC_MODEL) r = a.data[g] - mdl.eval_safe(a.x[g]);
+                else if (SRC == SRC_GIVEN) r = a.data[g] - row[g];
+                else r = row[g];
+            }
             T_[idx + (idx >> 4)] = r;
         }
         __syncwarp();
@@ -191,17 +203,14 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg(RegArgs a) {
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = T_[lane * 17 + k];
         __syncwarp();
-        // four levels in registers
         int cnt = 16;                                  // values this lane holds
 #pragma unroll
         for (int l = 0; l < 4; l++) {
             v[cnt] = __shfl_down_sync(0xffffffffu, v[0], 1);
             v[cnt + 1] = __shfl_down_sync(0xffffffffu, v[1], 1);
             const int half = cnt >> 1;
-            // ownership: output o = lane*half + j of this block at this level
             const int64_t lev_pos0 = (g0 >> (l + 1)) + (int64_t)lane * half;
             const int64_t lev_n = a.n_in >> (l + 1);
-            const int own_limit = RADV >> (l + 1);
             double s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -209,17 +218,21 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg(RegArgs a) {
                     const double a0 = v[2 * j], a1 = v[2 * j + 1], a2 = v[2 * j + 2], a3 = v[2 * j + 3];
                     const double sm = fma(c3, a3, fma(c2, a2, fma(c1, a1, c0 * a0)));
                     const double d = fma(-c0, a3, fma(c1, a2, fma(-c2, a1, c3 * a0)));
-                    const bool own = (lane * half + j < own_limit) && (lev_pos0 + j < lev_n);
-                    s2 = fma(d, own ? d : 0.0, s2);
+                    if (INTERIOR) s2 = fma(d, d, s2);
+                    else s2 = fma(d, (lev_pos0 + j < lev_n) ? d : 0.0, s2);
                     v[j] = sm;                         // j <= 2j: safe in-place
                 }
             }
-            acc[l] += s2;
+            // an output belongs to the block that holds its first input: lanes 0..29
+            acc[l] += (lane < 30) ? s2 : 0.0;
             cnt = half;
         }
-        // v[0] = level-4 smooth output of lane (valid for lanes < 30)
         const int64_t o = (g0 >> 4) + lane;
-        if (live && lane < 30 && o < (a.n_in >> 4)) a.out[c * a.ldo + o] = v[0];
+        if (live && lane < 30 && (INTERIOR || o < (a.n_in >> 4))) a.out[c * a.ldo + o] = v[0];
+    };
+    for (int64_t b = b_begin; b < b_end; b++) {
+        if (b * RADV + RB <= a.n_in) do_block(b, std::true_type{});
+        else do_block(b, std::false_type{});
     }
 #pragma unroll
     for (int l = 0; l < 4; l++) {
