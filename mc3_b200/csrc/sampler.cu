@@ -10,24 +10,9 @@
 // Jump arithmetic uses explicit round-to-nearest mul/add/sub intrinsics (no FMA
 // contraction) so that, fed the reference's recorded draws (replay mode), the
 // proposed points equal numpy's elementwise results.
-#include "common.cuh"
+#include "sampler_dev.cuh"
 
 namespace {
-
-constexpr int MAXP = MC3B_MAX_PARS;
-
-struct Draws {                      // what one chain consumes in one generation
-    int64_t a, b, iz;
-    double usj, gs, u;
-};
-
-__device__ __forceinline__ void box_muller(double u1, double u2, double& n0, double& n1) {
-    const double r = sqrt(-2.0 * log(1.0 - u1));     // 1-u1 in (0,1]
-    double s, c;
-    sincospi(2.0 * u2, &s, &c);
-    n0 = r * c;
-    n1 = r * s;
-}
 
 template <bool REPLAY>
 __global__ void __launch_bounds__(128) k_propose(mc3b_sampler_t S, mc3b_draws_t D, int64_t gen, int64_t zsize,
@@ -38,118 +23,7 @@ __global__ void __launch_bounds__(128) k_propose(mc3b_sampler_t S, mc3b_draws_t 
         gen = *S.gen_dev;
         zsize = S.M0 + (gen / S.thinning) * S.nchains;
     }
-    const int nfree = S.nfree, npars = S.npars;
-    const double* x = S.X + c * nfree;
-    double jump[MAXP], nrm[MAXP];
-    Draws dr;
-    dr.iz = -1; dr.usj = 1.0; dr.gs = 0.0;
-
-    if (REPLAY) {
-        for (int j = 0; j < nfree; j++) nrm[j] = D.normal[j];
-        dr.a = dr.b = 0;
-        if (S.sampler != MC3B_MRW) { dr.a = D.a[c]; dr.b = D.b[c]; }
-        if (S.sampler == MC3B_SNOOKER) { dr.iz = D.iz[c]; dr.usj = D.usj[c]; dr.gs = D.gs[c]; }
-        dr.u = D.u[c];
-    } else {
-        const Philox ph(S.seed);
-        const uint32_t cid = (uint32_t)c, g0 = (uint32_t)gen, g1 = (uint32_t)((uint64_t)gen >> 32);
-        const uint4 w0 = ph(cid, 0u, g0, g1), w1 = ph(cid, 1u, g0, g1), w2 = ph(cid, 2u, g0, g1);
-        if (S.sampler == MC3B_DEMC) {               // chain.py:223-229
-            int64_t r1 = 1 + ubelow(w0.x, w0.y, S.nchains - 1);
-            if (r1 == c) r1 = 0;
-            int64_t r2 = (r1 + 2 + ubelow(w0.z, w0.w, S.nchains - 2)) % S.nchains;
-            if (r2 == c) r2 = (r1 + 1) % S.nchains;
-            dr.a = r1; dr.b = r2;
-        } else if (S.sampler == MC3B_SNOOKER) {     // chain.py:197-203
-            int64_t i1 = ubelow(w0.x, w0.y, zsize);
-            int64_t i2 = 1 + ubelow(w0.z, w0.w, zsize - 1);
-            if (i2 == i1) i2 = 0;
-            dr.a = i1; dr.b = i2;
-            dr.usj = u01(w1.x, w1.y);
-            dr.gs = 1.2 + u01(w1.z, w1.w);
-            dr.iz = ubelow(w2.x, w2.y, zsize);
-        } else {
-            dr.a = dr.b = 0;
-        }
-        dr.u = u01(w2.z, w2.w);
-        for (int j = 0; j < nfree; j += 2) {        // per-chain support draw
-            const uint4 w = ph(cid, 3u + (uint32_t)(j >> 1), g0, g1);
-            double n0, n1;
-            box_muller(u01(w.x, w.y), u01(w.z, w.w), n0, n1);
-            nrm[j] = n0 * S.pstep[S.ifree[j]];
-            if (j + 1 < nfree) nrm[j + 1] = n1 * S.pstep[S.ifree[j + 1]];
-        }
-    }
-
-    double mrfactor = 1.0;
-    bool sjump = false;
-    const double* zrow = nullptr;
-    if (S.sampler == MC3B_SNOOKER) {
-        const double* z1 = S.Z + dr.a * nfree;
-        const double* z2 = S.Z + dr.b * nfree;
-        sjump = dr.usj < 0.1;
-        if (sjump) {                                 // chain.py:202-213
-            zrow = S.Z + dr.iz * nfree;
-            bool same = true;
-            for (int j = 0; j < nfree; j++) same = same && (zrow[j] == x[j]);
-            if (same) {
-                for (int j = 0; j < nfree; j++) jump[j] = __dmul_rn(dr.gs, __dsub_rn(z2[j], z1[j]));
-            } else {
-                double zp1 = 0.0, zp2 = 0.0, dd = 0.0;
-                for (int j = 0; j < nfree; j++) {
-                    const double dz = __dsub_rn(x[j], zrow[j]);
-                    zp1 = __dadd_rn(zp1, __dmul_rn(z1[j], dz));
-                    zp2 = __dadd_rn(zp2, __dmul_rn(z2[j], dz));
-                    dd = __dadd_rn(dd, __dmul_rn(dz, dz));
-                }
-                const double f = __dmul_rn(dr.gs, __dsub_rn(zp1, zp2));
-                for (int j = 0; j < nfree; j++)
-                    jump[j] = __ddiv_rn(__dmul_rn(f, __dsub_rn(x[j], zrow[j])), dd);
-            }
-        } else {                                     // chain.py:214-217
-            for (int j = 0; j < nfree; j++)
-                jump[j] = __dadd_rn(__dmul_rn(S.gamma, __dsub_rn(z1[j], z2[j])), __dmul_rn(S.fepsilon, nrm[j]));
-        }
-    } else if (S.sampler == MC3B_DEMC) {             // chain.py:230-232
-        const double* x1 = S.X + dr.a * nfree;
-        const double* x2 = S.X + dr.b * nfree;
-        for (int j = 0; j < nfree; j++)
-            jump[j] = __dadd_rn(__dmul_rn(S.gamma, __dsub_rn(x1[j], x2[j])), __dmul_rn(S.fepsilon, nrm[j]));
-    } else {                                         // mrw, chain.py:219-220
-        for (int j = 0; j < nfree; j++) jump[j] = nrm[j];
-    }
-
-    // chain.py:235-247 -- propose, bounds, shared parameters
-    double* np_ = S.nextp + c * npars;
-    for (int k = 0; k < npars; k++) np_[k] = S.params0[k];
-    int inb = 1;
-    for (int j = 0; j < nfree; j++) {
-        const int k = S.ifree[j];
-        double v = __dadd_rn(x[j], jump[j]);
-        if (S.reflect) {                             // opt-in, non-reference behaviour
-            const double lo = S.pmin[k], hi = S.pmax[k];
-            for (int it = 0; it < 8 && (v < lo || v > hi); it++) v = v < lo ? 2.0 * lo - v : 2.0 * hi - v;
-        }
-        np_[k] = v;
-        if (v < S.pmin[k] || v > S.pmax[k]) {
-            inb = 0;
-            atomicAdd(&S.outbounds[j], 1);
-        }
-    }
-    for (int k = 0; k < npars; k++)
-        if (S.pstep[k] < 0.0) np_[k] = np_[-(int)S.pstep[k] - 1];
-    if (sjump && inb) {                              // chain.py:251-255
-        double cn = 0.0, nn = 0.0;
-        for (int j = 0; j < nfree; j++) {
-            const double dc = __dsub_rn(x[j], zrow[j]), dn = __dsub_rn(np_[S.ifree[j]], zrow[j]);
-            cn = __dadd_rn(cn, __dmul_rn(dc, dc));
-            nn = __dadd_rn(nn, __dmul_rn(dn, dn));
-        }
-        mrfactor = pow(nn / cn, 0.5 * (nfree - 1));
-    }
-    S.mrfactor[c] = mrfactor;
-    S.u[c] = dr.u;
-    S.inb[c] = inb;
+    propose_chain<REPLAY>(S, D, gen, zsize, c);
 }
 
 __global__ void __launch_bounds__(128) k_metropolis(mc3b_sampler_t S, const double* partial, int64_t ldpartial, int nsplit,
@@ -161,46 +35,7 @@ __global__ void __launch_bounds__(128) k_metropolis(mc3b_sampler_t S, const doub
         gen = *S.gen_dev;
         zrow0 = ((gen + 1) % S.thinning == 0) ? S.M0 + ((gen + 1) / S.thinning - 1) * S.nchains : -1;
     }
-    const int nfree = S.nfree, npars = S.npars;
-    double* x = S.X + c * nfree;
-    double cur = S.chisq_cur[c];
-    if (S.inb[c]) {
-        const double* np_ = S.nextp + c * npars;
-        double nxt = 0.0;
-        for (int s = 0; s < nsplit; s++) nxt += partial[(int64_t)s * ldpartial + (c - c_off)];
-        if (S.prior != nullptr) {                    // stats.py:208-216 + stats.h:90-109
-            double pr = 0.0;
-            for (int k = 0; k < npars; k++) {
-                const double lo = S.priorlow[k], up = S.priorup[k];
-                if (lo > 0.0 && up > 0.0) {
-                    const double off = np_[k] - S.prior[k];
-                    const double t = off / (off > 0.0 ? up : lo);
-                    pr += t * t;
-                }
-            }
-            nxt += pr;
-        }
-        const double ratio = exp(0.5 * (cur - nxt)) * S.mrfactor[c];
-        if (ratio > S.u[c]) {                        // chain.py:257-274 (NaN rejects)
-            for (int j = 0; j < nfree; j++) x[j] = np_[S.ifree[j]];
-            cur = nxt;
-            S.chisq_cur[c] = nxt;
-            S.naccept[c] += 1;
-            if (nxt < S.best_chisq[c]) {
-                S.best_chisq[c] = nxt;
-                S.best_gen[c] = gen;
-                for (int j = 0; j < nfree; j++) S.best_x[c * nfree + j] = x[j];
-            }
-        }
-    }
-    if (zrow0 >= 0) {                                // chain.py:276-289
-        const int64_t row = zrow0 + c;
-        if (row < S.zlen) {
-            for (int j = 0; j < nfree; j++) S.Z[row * nfree + j] = x[j];
-            S.log_post[row] = -0.5 * cur;
-            S.zchain[row] = (int32_t)c;
-        }
-    }
+    metropolis_chain(S, partial, ldpartial, nsplit, c_off, gen, zrow0, c);
 }
 
 __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kickoff, int64_t ntrials, int64_t round,

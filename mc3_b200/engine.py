@@ -199,6 +199,10 @@ class Population:
         self.bestp0 = np.copy(params)     # best of the initial population
         self.best_log_post0 = -np.inf
 
+        # small populations run inside one persistent CTA (csrc/small.cu)
+        self.small = (self.kind == 'builtin' and not self.wlike and world == 1
+                      and self.dtype == _lib.F64 and self.nchains <= 64
+                      and self.ndata <= 32768 and not os.environ.get('MC3B_NO_SMALL'))
         self._plans = {}
         self._work = {}
         self._graph = None
@@ -449,6 +453,20 @@ class Population:
         if use_graph is None:
             use_graph = self.kind == 'builtin' and not \
                 (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker')
+        if use_graph and self.small:
+            # launch-latency-bound population: all generations inside one resident CTA
+            scratch = self._workspace('small', (self.nchains,))
+            done = 0
+            while done < ngen:
+                step = min(ngen - done, 200000)
+                _lib.call('mc3b_run_small', ctypes.byref(self.S), self.func.model_id,
+                          self.nmodel, self.d_x.data_ptr(), self.d_data.data_ptr(),
+                          self.d_invsig.data_ptr(), self.ndata, scratch.data_ptr(),
+                          self.gen + done, step, _lib.stream_ptr())
+                done += step
+            self.launches += 1
+            self.gen += ngen
+            return
         if not use_graph:
             for g in range(self.gen, self.gen + ngen):
                 self._generation(g)

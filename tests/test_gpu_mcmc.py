@@ -265,3 +265,37 @@ def test_gelman_rubin_device_matches_oracle(mc3):
     want = ok.gelman_rubin(out['posterior'], out['zchain'], 20)
     got = mc3.stats.gelman_rubin(out['posterior'], out['zchain'], 20)
     np.testing.assert_allclose(got, want, rtol=1e-10)
+    # the hub's own path: lock-step row formula on the device-resident history
+    from mc3_b200.mcmc_driver import mcmc
+    o2 = mcmc(p['data'], p['uncert'], mc3.models.polynomial, p['params'], [p['x']], {},
+              p['pmin'], p['pmax'], p['pstep'], p['prior'], p['priorlow'], p['priorup'],
+              40, None, 40*120, 'demc', False, None, True, 0.0, 0.5, 40, 2, 1.0, 0.0,
+              10, 'normal', None, False, mc3.Log(verb=-1), None, None, seed=6,
+              return_population=True)
+    pop = o2['_population']
+    zburn = o2['burnin']
+    assert zburn == 20 and pop.thinned_done() == 60
+    np.testing.assert_allclose(pop.gelman_rubin(zburn),
+                               ok.gelman_rubin(o2['posterior'], o2['zchain'], zburn), rtol=1e-10)
+
+
+@pytest.mark.parametrize('sampler', pb.SAMPLERS)
+def test_persistent_small_kernel_matches_per_generation_kernels(mc3, sampler):
+    """Small populations run inside one resident CTA (mc3b_run_small); the same
+    seed through the per-generation kernels (use_graph=False) gives the same
+    trajectory -- only the chi-squared summation order differs."""
+    p = pb.mcmc_case('sine')
+    kw = dict(data=p['data'], uncert=p['uncert'], func=mc3.models.sinusoid,
+              params=p['params'], indparams=[p['x']], pstep=p['pstep'], pmin=p['pmin'],
+              pmax=p['pmax'], prior=p['prior'], priorlow=p['priorlow'],
+              priorup=p['priorup'], sampler=sampler, nchains=8, nsamples=8*400,
+              burnin=20, thinning=2, fepsilon=0.01, seed=13, log=mc3.Log(verb=-1))
+    a = mc3.sample(**kw)                       # persistent kernel
+    b = mc3.sample(**kw, use_graph=False)      # propose / model_chisq / metropolis launches
+    assert np.array_equal(a['zchain'], b['zchain'])
+    same = np.all(a['posterior'] == b['posterior'], axis=1).mean()
+    assert same > 0.97, same
+    n = 8*20
+    np.testing.assert_allclose(a['posterior'][:n], b['posterior'][:n], rtol=1e-12)
+    np.testing.assert_allclose(a['log_post'][:n], b['log_post'][:n], rtol=1e-11)
+    assert abs(a['acceptance_rate'] - b['acceptance_rate']) < 2.0
