@@ -189,12 +189,11 @@ int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial,
  * model + chi-squared (a warp per chain), Metropolis step and history write per
  * generation, same Philox streams and lock-step semantics as mc3b_propose /
  * mc3b_model_chisq / mc3b_metropolis.  For launch-latency-bound problems (the
- * reference's everyday 7-21 chains on 1e2-1e4 points).  scratch: [nchains] fp64.
+ * reference's everyday 7-21 chains on 1e2-1e4 points).
  * Writes gen0+ngen to *s->gen_dev when it is set.  [host] s. */
 int mc3b_run_small(const mc3b_sampler_t* s, int model_id, int nmodel,
                    const double* x, const double* data, const double* invsig,
-                   int64_t n, double* scratch, int64_t gen0, int64_t ngen,
-                   void* stream);
+                   int64_t n, int64_t gen0, int64_t ngen, void* stream);
 
 /* Trial points of the initial population (mcmc_driver.py:229-262):
  * trial[t, :] = params0 with free entries drawn N(params0, pstep) (kickoff 0)

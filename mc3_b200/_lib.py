@@ -69,7 +69,7 @@ _SIGS = {
                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
     'mc3b_advance': (c_int, [ctypes.POINTER(SamplerStruct), c_vp]),
     'mc3b_run_small': (c_int, [ctypes.POINTER(SamplerStruct), c_int, c_int, c_vp, c_vp, c_vp,
-                               c_i64, c_vp, c_i64, c_i64, c_vp]),
+                               c_i64, c_i64, c_i64, c_vp]),
     'mc3b_init_trials': (c_int, [ctypes.POINTER(SamplerStruct), c_int, c_i64, c_i64,
                                  c_vp, c_vp, c_vp]),
     'mc3b_log_prior': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,

@@ -455,13 +455,12 @@ class Population:
                 (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker')
         if use_graph and self.small:
             # launch-latency-bound population: all generations inside one resident CTA
-            scratch = self._workspace('small', (self.nchains,))
             done = 0
             while done < ngen:
                 step = min(ngen - done, 200000)
                 _lib.call('mc3b_run_small', ctypes.byref(self.S), self.func.model_id,
                           self.nmodel, self.d_x.data_ptr(), self.d_data.data_ptr(),
-                          self.d_invsig.data_ptr(), self.ndata, scratch.data_ptr(),
+                          self.d_invsig.data_ptr(), self.ndata,
                           self.gen + done, step, _lib.stream_ptr())
                 done += step
             self.launches += 1

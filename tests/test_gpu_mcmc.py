@@ -155,8 +155,8 @@ def test_same_seed_same_bytes_and_graph_equals_eager(mc3):
               params=p['params'], indparams=[p['x']], pstep=p['pstep'],
               pmin=p['pmin'], pmax=p['pmax'], prior=p['prior'],
               priorlow=p['priorlow'], priorup=p['priorup'], sampler='demc',
-              nchains=64, nsamples=64*50, burnin=10, thinning=2, fepsilon=0.01,
-              seed=3, log=mc3.Log(verb=-1))
+              nchains=128, nsamples=128*50, burnin=10, thinning=2, fepsilon=0.01,
+              seed=3, log=mc3.Log(verb=-1))    # > 64 chains: per-generation kernels
     a = mc3.sample(**kw, use_graph=True)
     b = mc3.sample(**kw, use_graph=True)
     c = mc3.sample(**kw, use_graph=False)
