@@ -242,6 +242,89 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg(RegArgs a) {
     }
 }
 
+// Built-in models: the 8 chains of a CTA walk the same blocks, so x and data are
+// staged ONCE per CTA (double-buffered, padded rows of 18 so that a lane's 16
+// consecutive values are conflict-free 16-byte reads) and every warp evaluates
+// its own chain's residuals straight into the lane-contiguous registers -- no
+// per-warp transpose.  L1/shared-memory wavefronts per block and warp: ~80
+// instead of 128.
+constexpr int RPAD = 18;                         // doubles per 16-value row
+
+template <class M>
+__global__ void __launch_bounds__(CH * 32) k_dwt_reg_model(RegArgs a) {
+    __shared__ __align__(16) double sxd[2][2][32 * RPAD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t c = (int64_t)blockIdx.x * CH + warp;
+    const bool live = c < a.nchains;
+    if (!live) c = a.nchains - 1;
+    M mdl;
+    mdl.load(a.params + c * a.ldp);
+    const double c0 = kC[0], c1 = kC[1], c2 = kC[2], c3 = kC[3];
+    const int64_t mask = a.n_in - 1;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t b_begin = (int64_t)blockIdx.y * a.blocks_per_span;
+    int64_t b_end = b_begin + a.blocks_per_span;
+    if (b_end > a.nblocks) b_end = a.nblocks;
+    auto fill = [&](int64_t b, int buf) {
+        const int64_t g0 = b * RADV;
+#pragma unroll
+        for (int q = 0; q < RB / (CH * 32); q++) {
+            const int idx = q * CH * 32 + threadIdx.x;
+            const int64_t g = (g0 + idx) & mask;
+            const int pos = (idx >> 4) * RPAD + (idx & 15);
+            sxd[buf][0][pos] = a.x[g];
+            sxd[buf][1][pos] = a.data[g];
+        }
+    };
+    if (b_begin < b_end) fill(b_begin, 0);
+    for (int64_t b = b_begin; b < b_end; b++) {
+        const int buf = (int)((b - b_begin) & 1);
+        __syncthreads();                             // tile b is complete; tile b-1 is no longer read
+        if (b + 1 < b_end) fill(b + 1, buf ^ 1);
+        const int64_t g0 = b * RADV;
+        const bool interior = g0 + RB <= a.n_in;
+        double v[18];
+        const double2* px = reinterpret_cast<const double2*>(&sxd[buf][0][lane * RPAD]);
+        const double2* pd = reinterpret_cast<const double2*>(&sxd[buf][1][lane * RPAD]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double2 xv = px[k], dv = pd[k];
+            v[2 * k] = dv.x - mdl.eval_safe(xv.x);
+            v[2 * k + 1] = dv.y - mdl.eval_safe(xv.y);
+        }
+        int cnt = 16;
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            v[cnt] = __shfl_down_sync(0xffffffffu, v[0], 1);
+            v[cnt + 1] = __shfl_down_sync(0xffffffffu, v[1], 1);
+            const int half = cnt >> 1;
+            const int64_t lev_pos0 = (g0 >> (l + 1)) + (int64_t)lane * half;
+            const int64_t lev_n = a.n_in >> (l + 1);
+            double s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (j < half) {
+                    const double a0 = v[2 * j], a1 = v[2 * j + 1], a2 = v[2 * j + 2], a3 = v[2 * j + 3];
+                    const double sm = fma(c3, a3, fma(c2, a2, fma(c1, a1, c0 * a0)));
+                    const double d = fma(-c0, a3, fma(c1, a2, fma(-c2, a1, c3 * a0)));
+                    s2 = fma(d, (interior || lev_pos0 + j < lev_n) ? d : 0.0, s2);
+                    v[j] = sm;
+                }
+            }
+            acc[l] += (lane < 30) ? s2 : 0.0;
+            cnt = half;
+        }
+        const int64_t o = (g0 >> 4) + lane;
+        if (live && lane < 30 && o < (a.n_in >> 4)) a.out[c * a.ldo + o] = v[0];
+    }
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        double t = acc[l];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0 && live) a.sums[(c * MAXLEV + (a.lev0 + l)) * MAXSPAN + blockIdx.y] = t;
+    }
+}
+
 struct LastArgs {
     const double* params; int64_t ldp; int npars; int64_t nchains;
     const double* x; const double* data;
@@ -416,7 +499,8 @@ static int dwt_run(const Schedule& sc, int kbits, const double* params, int64_t 
             // spans actually needed with whole blocks per span
             const int spans = (int)ceil_div64(sc.nblocks[p], sc.tps[p]);
             dim3 grid(groups, (unsigned)spans);
-            if (p == 0) k_dwt_reg<SRC, M><<<grid, CH * 32, 0, st>>>(r);
+            if (p == 0 && SRC == SRC_MODEL) k_dwt_reg_model<M><<<grid, CH * 32, 0, st>>>(r);
+            else if (p == 0) k_dwt_reg<SRC, M><<<grid, CH * 32, 0, st>>>(r);
             else k_dwt_reg<SRC_ARRAY, BoxModel<double>><<<grid, CH * 32, 0, st>>>(r);
             MC3B_CHECK_LAUNCH("k_dwt_reg");
             for (int l = 0; l < 4; l++) la.spans_of_level[lev0 + l] = spans;

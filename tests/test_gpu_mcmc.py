@@ -299,3 +299,30 @@ def test_persistent_small_kernel_matches_per_generation_kernels(mc3, sampler):
     np.testing.assert_allclose(a['posterior'][:n], b['posterior'][:n], rtol=1e-12)
     np.testing.assert_allclose(a['log_post'][:n], b['log_post'][:n], rtol=1e-11)
     assert abs(a['acceptance_rate'] - b['acceptance_rate']) < 2.0
+
+
+def test_reflect_mode_folds_proposals_inside_bounds(mc3):
+    """Opt-in, non-reference behaviour (BASELINE north_star wording): out-of-bounds
+    proposals are folded back instead of rejected.  Nothing is ever counted out of
+    bounds, every sample respects the bounds, and the posterior still matches."""
+    p = pb.mcmc_case('sine')
+    kw = dict(data=p['data'], uncert=p['uncert'], func=mc3.models.sinusoid,
+              params=p['params'], indparams=[p['x']], pstep=p['pstep'], pmin=p['pmin'],
+              pmax=p['pmax'], sampler='demc', nchains=128, nsamples=128*300, burnin=100,
+              fepsilon=0.01, seed=8, log=mc3.Log(verb=-1))
+    from mc3_b200.mcmc_driver import mcmc
+    outs = {}
+    for reflect in (False, True):
+        o = mcmc(p['data'], p['uncert'], mc3.models.sinusoid, p['params'], [p['x']], {},
+                 p['pmin'], p['pmax'], p['pstep'], None, None, None, 128, None, 128*300,
+                 'demc', False, None, False, 0.0, 0.5, 100, 1, 1.0, 0.01, 10, 'normal',
+                 None, False, mc3.Log(verb=-1), None, None, seed=8, reflect=reflect,
+                 return_population=True)
+        outs[reflect] = (o, o['_population'].counters()['outbounds'])
+    assert outs[False][1].sum() > 0            # the bounds of this case do get hit
+    assert outs[True][1].sum() == 0
+    post = outs[True][0]['posterior']
+    assert np.all(post >= p['pmin'][None, :]) and np.all(post <= p['pmax'][None, :])
+    a = outs[False][0]['posterior'][128*100:]
+    b = post[128*100:]
+    assert np.all(np.abs(a.mean(axis=0) - b.mean(axis=0)) < 0.5*a.std(axis=0))
