@@ -139,6 +139,16 @@ typedef struct mc3b_sampler {
     int64_t* best_gen;           /* [nchains] generation where it was reached      */
     int64_t* gen_dev;            /* device generation counter (graph mode) or NULL */
     int64_t thinning;            /* generations per history row (graph mode)       */
+    /* Multi-GPU exchange fused into the Metropolis kernel (peer stores over NVLink).
+     * X_peers: NULL, or [world] device pointers (in device memory) to every
+     * device's [2, nchains, nfree] population buffer; generation g reads half g&1
+     * and k_metropolis writes every chain's next state (moved or not) into half
+     * (g+1)&1 of EVERY device, so one cross-device barrier per generation orders
+     * the exchange (X is then ignored).  Z_peers: NULL, or [world] pointers to
+     * every device's history Z; thinned rows are stored to all of them (snooker). */
+    double* const* X_peers;
+    double* const* Z_peers;
+    int32_t world, rank;
 } mc3b_sampler_t;
 
 /* Recorded random stream of one generation (replay mode), indexed by global

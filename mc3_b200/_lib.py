@@ -37,6 +37,7 @@ class SamplerStruct(ctypes.Structure):
         ('naccept', c_vp), ('outbounds', c_vp), ('best_chisq', c_vp),
         ('best_x', c_vp), ('best_gen', c_vp),
         ('gen_dev', c_vp), ('thinning', c_i64),
+        ('X_peers', c_vp), ('Z_peers', c_vp), ('world', c_i32), ('rank', c_i32),
     ]
 
 

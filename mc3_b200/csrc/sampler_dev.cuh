@@ -25,7 +25,9 @@ template <bool REPLAY>
 __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,
                                               int64_t zsize, int64_t c) {
     const int nfree = S.nfree, npars = S.npars;
-    const double* x = S.X + c * nfree;
+    // population as of the start of this generation (peer mode: half gen & 1)
+    const double* Xg = S.X_peers ? S.X_peers[S.rank] + (gen & 1) * S.nchains * nfree : S.X;
+    const double* x = Xg + c * nfree;
     double jump[MAXP], nrm[MAXP];
     Draws dr;
     dr.iz = -1; dr.usj = 1.0; dr.gs = 0.0;
@@ -97,8 +99,8 @@ __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3
                 jump[j] = __dadd_rn(__dmul_rn(S.gamma, __dsub_rn(z1[j], z2[j])), __dmul_rn(S.fepsilon, nrm[j]));
         }
     } else if (S.sampler == MC3B_DEMC) {             // chain.py:230-232
-        const double* x1 = S.X + dr.a * nfree;
-        const double* x2 = S.X + dr.b * nfree;
+        const double* x1 = Xg + dr.a * nfree;
+        const double* x2 = Xg + dr.b * nfree;
         for (int j = 0; j < nfree; j++)
             jump[j] = __dadd_rn(__dmul_rn(S.gamma, __dsub_rn(x1[j], x2[j])), __dmul_rn(S.fepsilon, nrm[j]));
     } else {                                         // mrw, chain.py:219-220
@@ -142,10 +144,13 @@ __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3
 __device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, const double* partial, int64_t ldpartial,
                                                  int nsplit, int64_t c_off, int64_t gen, int64_t zrow0, int64_t c) {
     const int nfree = S.nfree, npars = S.npars;
-    double* x = S.X + c * nfree;
+    const bool peer = S.X_peers != nullptr;
+    const int64_t half = S.nchains * nfree;
+    double* x = peer ? S.X_peers[S.rank] + (gen & 1) * half + c * nfree : S.X + c * nfree;
     double cur = S.chisq_cur[c];
+    bool accept = false;
+    const double* np_ = S.nextp + c * npars;
     if (S.inb[c]) {
-        const double* np_ = S.nextp + c * npars;
         double nxt = 0.0;
         for (int s = 0; s < nsplit; s++) nxt += partial[(int64_t)s * ldpartial + (c - c_off)];
         if (S.prior != nullptr) {                    // stats.py:208-216 + stats.h:90-109
@@ -162,24 +167,41 @@ __device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, const 
         }
         const double ratio = exp(0.5 * (cur - nxt)) * S.mrfactor[c];
         if (ratio > S.u[c]) {                        // chain.py:257-274 (NaN rejects)
-            for (int j = 0; j < nfree; j++) x[j] = np_[S.ifree[j]];
+            accept = true;
             cur = nxt;
             S.chisq_cur[c] = nxt;
             S.naccept[c] += 1;
             if (nxt < S.best_chisq[c]) {
                 S.best_chisq[c] = nxt;
                 S.best_gen[c] = gen;
-                for (int j = 0; j < nfree; j++) S.best_x[c * nfree + j] = x[j];
+                for (int j = 0; j < nfree; j++) S.best_x[c * nfree + j] = np_[S.ifree[j]];
             }
         }
     }
-    if (zrow0 >= 0) {                                // chain.py:276-289
-        const int64_t row = zrow0 + c;
-        if (row < S.zlen) {
-            for (int j = 0; j < nfree; j++) S.Z[row * nfree + j] = x[j];
-            S.log_post[row] = -0.5 * cur;
-            S.zchain[row] = (int32_t)c;
+    const bool write = zrow0 >= 0 && zrow0 + c < S.zlen;
+    const int64_t row = zrow0 + c;
+    if (!peer) {
+        if (accept)
+            for (int j = 0; j < nfree; j++) x[j] = np_[S.ifree[j]];
+        if (write)
+            for (int j = 0; j < nfree; j++) S.Z[row * nfree + j] = x[j];      // chain.py:276-289
+    } else {
+        // next state of this chain into half (gen+1)&1 of EVERY device (NVLink
+        // peer stores); thinned rows likewise when the history is shared
+        const int64_t dst = ((gen + 1) & 1) * half + c * nfree;
+        for (int j = 0; j < nfree; j++) {
+            const double v = accept ? np_[S.ifree[j]] : x[j];
+            for (int p = 0; p < S.world; p++) S.X_peers[p][dst + j] = v;
+            if (write) {
+                if (S.Z_peers) { for (int p = 0; p < S.world; p++) S.Z_peers[p][row * nfree + j] = v; }
+                else S.Z[row * nfree + j] = v;
+            }
         }
+        __threadfence_system();
+    }
+    if (write) {
+        S.log_post[row] = -0.5 * cur;
+        S.zchain[row] = (int32_t)c;
     }
 }
 

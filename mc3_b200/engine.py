@@ -179,9 +179,26 @@ class Population:
 
         # ---- population state ----
         n = self.nchains
-        self.X = torch.zeros((n, nfree), **f64)
+        # Multi-GPU chain partition, opt-in peer-memory exchange (MC3B_P2P=1):
+        # population (and, for snooker, history) live in symmetric memory so that
+        # k_metropolis stores every chain's next state straight into all peers over
+        # NVLink; a signal-pad barrier per generation replaces the NCCL all-gather.
+        # Measured at 2 GPUs: 0.3108 vs 0.3151 ms per generation (config 2).  Off by
+        # default in round 1: one of four 2-GPU test launches stalled in it.
+        self.p2p = None
+        self._Xsym = None
+        if world > 1 and self.shard == 'chains' and os.environ.get('MC3B_P2P') == '1':
+            try:
+                self.p2p = self._setup_p2p(n, nfree)
+            except Exception as e:                      # no P2P / symmetric memory: NCCL path
+                if rank == 0:
+                    print(f'mc3_b200: peer-memory exchange unavailable ({e}); using NCCL all-gather')
+                self.p2p = None
+        if self.p2p is None:
+            self._X = torch.zeros((n, nfree), **f64)
         self.chisq_cur = torch.zeros(n, **f64)
-        self.Z = torch.zeros((self.zlen, nfree), **f64)
+        if self.p2p is None or sampler != 'snooker':
+            self.Z = torch.zeros((self.zlen, nfree), **f64)
         self.log_post = torch.zeros(self.zlen, **f64)
         self.zchain = torch.full((self.zlen,), -1, dtype=torch.int32, device=self.dev)
         self.nextp = torch.zeros((n, npars), **f64)
@@ -228,6 +245,10 @@ class Population:
         S.fepsilon = 0.0
         S.seed = self.seed
         S.X, S.chisq_cur = self.X.data_ptr(), self.chisq_cur.data_ptr()
+        S.world, S.rank = self.world, self.rank
+        if self.p2p is not None:
+            S.X_peers = self.p2p['x_ptrs']
+            S.Z_peers = self.p2p.get('z_ptrs')
         S.Z, S.log_post, S.zchain = (self.Z.data_ptr(), self.log_post.data_ptr(),
                                      self.zchain.data_ptr())
         S.zlen, S.M0 = self.zlen, self.M0
@@ -238,6 +259,36 @@ class Population:
         S.best_gen = self.best_gen.data_ptr()
         S.gen_dev, S.thinning = self.gen_dev.data_ptr(), self.thinning
         return S
+
+    @property
+    def X(self):
+        """Current population [nchains, nfree] (peer mode: the half of this generation)."""
+        if self._Xsym is not None:
+            return self._Xsym[self.gen & 1]
+        return self._X
+
+    def _setup_p2p(self, n, nfree):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = self.group if self.group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(grp.group_name)
+        except Exception:
+            pass
+        self._Xsym = symm.empty((2, n, nfree), dtype=torch.float64, device=self.dev)
+        self._Xsym.zero_()
+        xh = symm.rendezvous(self._Xsym, grp)
+        out = {'x_hdl': xh, 'x_ptrs': int(xh.buffer_ptrs_dev)}
+        if self.sampler == 'snooker':
+            self.Z = symm.empty((self.zlen, nfree), dtype=torch.float64, device=self.dev)
+            self.Z.zero_()
+            zh = symm.rendezvous(self.Z, grp)
+            out['z_hdl'] = zh
+            out['z_ptrs'] = int(zh.buffer_ptrs_dev)
+        torch.cuda.synchronize(self.dev)
+        xh.barrier(channel=0)                   # nobody stores into a peer before its buffers are zeroed
+        torch.cuda.synchronize(self.dev)
+        return out
 
     def set_jump_scales(self, fgamma, fepsilon):
         self.S.gamma = float(fgamma)*2.38/np.sqrt(2*self.nfree)   # chain.py:175
@@ -386,7 +437,13 @@ class Population:
         assert Z0.shape == (self.M0, self.nfree)
         self.Z[:self.M0] = Z0
         self.log_post[:self.M0] = lp0
-        self.X.copy_(self.Z[:self.nchains])
+        if self._Xsym is not None:
+            self._Xsym[0].copy_(self.Z[:self.nchains])
+            self._Xsym[1].copy_(self.Z[:self.nchains])
+            torch.cuda.synchronize(self.dev)    # peers may store into our halves after this barrier only
+            self.p2p['x_hdl'].barrier(channel=0)
+        else:
+            self._X.copy_(self.Z[:self.nchains])
         self.chisq_cur.copy_(-2.0*self.log_post[:self.nchains])
         iz = int(torch.argmax(lp0))                  # mcmc_driver.py:273-275
         self.best_log_post0 = float(lp0[iz])
@@ -421,13 +478,18 @@ class Population:
             self.launches += 1
 
     def _exchange(self, gen):
-        """Per-generation population exchange across devices:
-        demc needs every chain's current state, snooker the new history rows."""
+        """Per-generation population exchange across devices: demc
+        needs every chain's current state, snooker the new history rows.  Peer
+        mode: the stores were issued by k_metropolis; one signal-pad barrier
+        orders them.  NCCL mode: all-gather of X (demc) / of the new rows (snooker)."""
+        if self.p2p is not None:
+            self.p2p['x_hdl'].barrier(channel=0)
+            return
         if self.sampler == 'demc':
-            allgather_rows(self.X, self.chain0, self.nlocal, self.group)
+            allgather_rows(self._X, self.chain0, self.nlocal, self.group)
         elif self.sampler == 'snooker':
             if gen < 0:
-                raise _lib.Mc3bError('multi-GPU snooker runs host-driven generations')
+                raise _lib.Mc3bError('multi-GPU snooker over NCCL runs host-driven generations')
             r0 = self._zrow0(gen)
             if r0 >= 0:
                 allgather_rows(self.Z[r0:r0 + self.nchains], self.chain0,
@@ -452,7 +514,8 @@ class Population:
             return
         if use_graph is None:
             use_graph = self.kind == 'builtin' and not \
-                (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker')
+                (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker'
+                 and self.p2p is None)
         if use_graph and self.small:
             # launch-latency-bound population: all generations inside one resident CTA
             done = 0
@@ -554,6 +617,8 @@ class Population:
         if self.shard == 'data':
             return
         for t in (self.Z, self.log_post, self.zchain):
+            if t is self.Z and self.p2p is not None and 'z_hdl' in self.p2p:
+                continue                     # rows were stored to every device as they were written
             gather_history(t, self.M0, self.thinned_done(), self.nchains,
                            self.rank, self.world, self.group)
 

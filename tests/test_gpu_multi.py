@@ -62,7 +62,7 @@ def _launch(world, sampler, shard):
              for r in range(world)]
     for pr in procs:
         pr.start()
-    res = q.get(timeout=240)
+    res = q.get(timeout=100)
     for pr in procs:
         pr.join(60)
     return res
