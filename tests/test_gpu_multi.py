@@ -47,6 +47,8 @@ def _run(rank, world, port, sampler, shard, q):
     if rank == 0:
         q.put({k: out[k] for k in ('posterior', 'zchain', 'log_post', 'bestp',
                                    'acceptance_rate', 'medianp')})
+        q.close()
+        q.join_thread()              # flush the payload before leaving without destructors
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
