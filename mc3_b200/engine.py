@@ -37,24 +37,20 @@ from . import _lib
 from .models import BuiltinModel, TorchModel, SINUSOID, SINUSOID_GRID
 from .parallel import chain_slice, allgather_rows, gather_history, sum_owned
 
-_PINNED = {}
 
 
 def to_host(t):
-    """Device tensor -> new numpy array through a cached pinned staging buffer
-    (pageable D2H of the 10-100 MB history costs several times the PCIe time)."""
+    """Device tensor -> numpy array backed by pinned host memory (pageable D2H
+    of the 10-100 MB history costs several times the PCIe time).  The array
+    owns its pinned block; torch's host allocator recycles it once the array
+    is dropped, so repeated runs pay no cudaHostAlloc and no second copy."""
     if t.numel() == 0 or t.numel()*t.element_size() < (1 << 20):
         return t.cpu().numpy()
     t = t.contiguous()
-    key = t.dtype
-    buf = _PINNED.get(key)
-    if buf is None or buf.numel() < t.numel():
-        buf = torch.empty(t.numel(), dtype=t.dtype, pin_memory=True)
-        _PINNED[key] = buf
-    view = buf[:t.numel()].view(t.shape)
-    view.copy_(t, non_blocking=True)
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    return view.numpy().copy()
+    return buf.numpy()
 
 
 _DT = {'f64': _lib.F64, 'f32': _lib.F32, np.float64: _lib.F64, np.float32: _lib.F32}
@@ -513,7 +509,10 @@ class Population:
         if ngen <= 0:
             return
         if use_graph is None:
-            use_graph = self.kind == 'builtin' and not \
+            # A generation with >= ~0.3 ms of device work hides its three host
+            # launches completely: skip the capture (10-15 ms) and run eagerly.
+            heavy = float(self.nlocal)*self.ndata > 2e8 and not self.small
+            use_graph = self.kind == 'builtin' and not heavy and not \
                 (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker'
                  and self.p2p is None)
         if use_graph and self.small:
