@@ -22,10 +22,26 @@
 
 namespace {
 
-constexpr int WARPS = 4;
+#ifndef MC3B_WARPS
+#define MC3B_WARPS 4
+#endif
+#ifndef MC3B_RESIDENT
+#define MC3B_RESIDENT 6
+#endif
+#ifndef MC3B_RESIDENT2
+#define MC3B_RESIDENT2 4
+#endif
+#ifndef MC3B_LOOP_UNROLL
+#define MC3B_LOOP_UNROLL 2
+#endif
+#ifndef MC3B_TILE_F64
+#define MC3B_TILE_F64 128
+#endif
+constexpr int WARPS = MC3B_WARPS;
 constexpr int STAGES = 3;
-constexpr int RESIDENT = 6;     // CTAs per SM the register budget is tuned for (ILP over occupancy)
-template <typename T> struct tilecfg { static constexpr int TILE = 128; };   // fp64: 128 beat 256 by 6% (finer balance)
+constexpr int LOOP_UNROLL = MC3B_LOOP_UNROLL;   // point groups of the inner loop unrolled together
+constexpr int RESIDENT = MC3B_RESIDENT;   // CTAs per SM the register budget is tuned for (ILP over occupancy)
+template <typename T> struct tilecfg { static constexpr int TILE = MC3B_TILE_F64; };   // fp64: 128 beat 256 by 6% (finer balance)
 template <> struct tilecfg<float> { static constexpr int TILE = 512; };
 
 template <typename T> struct ChisqArgs {
@@ -39,7 +55,7 @@ template <typename T> struct ChisqArgs {
 };
 
 template <class M, typename T, int LC, int CPT>
-__global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<T> a) {
+__global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESIDENT)) k_model_chisq(ChisqArgs<T> a) {
     constexpr int TILE = tilecfg<T>::TILE;
     constexpr int LP = 32 / LC;
     __shared__ __align__(128) T sx[STAGES][TILE];
@@ -58,7 +74,7 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
         if (c >= a.nchains) c = a.nchains - 1;      // idle lanes shadow the last chain
         if constexpr (M::TILE_STATE) {
             const double dx = ((double)a.x[a.n - 1] - (double)a.x[0]) / (double)(a.n - 1);
-            mdl[k].load(a.params + c * a.ldp, dx);
+            mdl[k].load(a.params + c * a.ldp, dx, TILE);
         } else {
             mdl[k].load(a.params + c * a.ldp);
         }
@@ -88,9 +104,21 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
         };
         if (threadIdx.x == 0)
             for (int s = 0; s < STAGES && s < nt; s++) issue(tb + s, s);
+        constexpr bool PM = premul_of<M>::value;
+        // PM: data tile <- data / sigma, once for all chains of the CTA.  Tile it+1 is
+        // scaled at the end of tile it, so that the stage-release barrier publishes it.
+        auto premul = [&](int64_t t) {
+            const int s1 = (int)(t % STAGES);
+            mbar_wait(&bar[s1], (uint32_t)((t / STAGES) & 1));
+            for (int i = threadIdx.x; i < TILE; i += WARPS * 32) sd[s1][i] *= sw[s1][i];
+        };
+        if constexpr (PM) {
+            if (nt > 0) premul(0);
+            __syncthreads();
+        }
         for (int64_t it = 0; it < nt; it++) {
             const int s = (int)(it % STAGES);
-            mbar_wait(&bar[s], (uint32_t)((it / STAGES) & 1));
+            if constexpr (!PM) mbar_wait(&bar[s], (uint32_t)((it / STAGES) & 1));
             constexpr int U = 4;                // points in flight per lane
             static_assert(TILE % (U * LP) == 0, "tile must hold whole groups");
             if constexpr (M::TILE_STATE) {
@@ -104,6 +132,7 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
 #pragma unroll
                 for (int u = 0; u < U; u++) uacc[k][u] = (T)0;
             }
+#pragma unroll(LOOP_UNROLL)
             for (int i = lp; i < TILE; i += U * LP) {
                 T x[U], y[U];
 #pragma unroll
@@ -113,7 +142,8 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
                     eval_points<M, T, U>(mdl[k], x, y, 0);
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const T r = (y[u] - sd[s][i + u * LP]) * sw[s][i + u * LP];
+                        const T r = PM ? fma(y[u], sw[s][i + u * LP], -sd[s][i + u * LP])
+                                       : (y[u] - sd[s][i + u * LP]) * sw[s][i + u * LP];
                         uacc[k][u] = fma(r, r, uacc[k][u]);
                     }
                 }
@@ -127,7 +157,8 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
                         mdl[k].clear();
                         tacc[k] = (T)0;
                         for (int i = lp; i < TILE; i += LP) {
-                            const T r = (mdl[k].eval_safe(sx[s][i]) - sd[s][i]) * sw[s][i];
+                            const T r = PM ? fma(mdl[k].eval_safe(sx[s][i]), sw[s][i], -sd[s][i])
+                                           : (mdl[k].eval_safe(sx[s][i]) - sd[s][i]) * sw[s][i];
                             tacc[k] = fma(r, r, tacc[k]);
                         }
                     }
@@ -135,8 +166,14 @@ __global__ void __launch_bounds__(WARPS * 32, RESIDENT) k_model_chisq(ChisqArgs<
             }
 #pragma unroll
             for (int k = 0; k < CPT; k++) acc[k] += (double)tacc[k];
+            if constexpr (PM) {
+                if (it + 1 < nt) premul(it + 1);
+            }
             __syncthreads();                    // everyone is done reading stage s
-            if (threadIdx.x == 0 && it + STAGES < nt) issue(tb + it + STAGES, s);
+            if (threadIdx.x == 0 && it + STAGES < nt) {
+                if constexpr (PM) fence_proxy_async();
+                issue(tb + it + STAGES, s);
+            }
         }
     } else {
         for (int64_t it = 0; it < nt; it++) {   // unaligned inputs: plain staged loads
@@ -204,7 +241,7 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     if (const char* e = getenv("MC3B_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 1;
     // whole waves of RESIDENT CTAs per SM (round to nearest: a few CTAs over one
     // wave cost a whole extra wave, so round down unless clearly closer to the next)
-    int64_t want = ((int64_t)sms * RESIDENT * waves) / s.groups;
+    int64_t want = ((int64_t)sms * (s.cpt == 2 ? MC3B_RESIDENT2 : RESIDENT) * waves) / s.groups;
     int64_t ns = want < 1 ? 1 : want;
     if (ns > nfull) ns = nfull;
     if (ns > MC3B_MAX_SPLIT) ns = MC3B_MAX_SPLIT;
@@ -236,9 +273,10 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
     MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
     if (model_id == MC3B_MODEL_SINUSOID_GRID) {
         if constexpr (std::is_same<T, double>::value) {
-            if (sh.lc == 32 && sh.cpt == 1 && a.use_tma && n >= 2) {
+            if (sh.lc == 32 && a.use_tma && n >= 2) {
                 dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
-                k_model_chisq<SineGridModel, double, 32, 1><<<grid, block, 0, st>>>(a);
+                if (sh.cpt == 2) k_model_chisq<SineGridModel, double, 32, 2><<<grid, block, 0, st>>>(a);
+                else k_model_chisq<SineGridModel, double, 32, 1><<<grid, block, 0, st>>>(a);
                 MC3B_CHECK_LAUNCH("k_model_chisq<grid>");
                 return MC3B_OK;
             }

@@ -74,6 +74,34 @@ __global__ void k_fma_const(int64_t iters, double* sink) {
     if (s == 123456.789) sink[0] = s;
 }
 
+//   5: every FMA reads three different vector registers that no neighbour shares
+//      (register-file operand bandwidth instead of pipe issue rate)
+//   6: two different vector registers + one shared multiplier
+template <int MODE>
+__global__ void __launch_bounds__(128, 6) k_fma_regs(int64_t iters, double* sink) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        a[k] = (double)(threadIdx.x + k) * 1e-3;
+        b[k] = 0.999999 + 1e-9 * (threadIdx.x + k);
+        c[k] = 1e-7 * (threadIdx.x + 3 * k + 1);
+    }
+    for (int64_t i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (MODE == 5) a[k] = fma(a[k], b[(k + j) & 7], c[(k + 3 * j + 1) & 7]);
+                else a[k] = fma(a[k], b[0], c[(k + 3 * j + 1) & 7]);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += a[k];
+    if (s == 123456.789) sink[0] = s;
+}
+
 extern "C" int mc3b_fma_peak_variant(int variant, int64_t iters, double* sink, double* flops, void* stream) {
     MC3B_CHECK_ARG(sink && flops && iters > 0, "bad arguments");
     int sms = mc3b_sm_count();
@@ -90,6 +118,10 @@ extern "C" int mc3b_fma_peak_variant(int variant, int64_t iters, double* sink, d
     } else if (variant == 4) {
         k_fma_const<1><<<sms * 8, 128, 0, (cudaStream_t)stream>>>(iters, sink);
         *flops = 2.0 * 8.0 * 1.0 * 128.0 * sms * 8.0 * (double)iters;
+    } else if (variant == 5 || variant == 6) {
+        if (variant == 5) k_fma_regs<5><<<sms * 6, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+        else k_fma_regs<6><<<sms * 6, 128, 0, (cudaStream_t)stream>>>(iters, sink);
+        *flops = 2.0 * 8.0 * 8.0 * 128.0 * sms * 6.0 * (double)iters;
     } else { mc3b_set_error("bad variant %d", variant); return MC3B_ERR_ARG; }
     MC3B_CHECK_LAUNCH("k_fma_const");
     return MC3B_OK;

@@ -10,5 +10,5 @@ def t(fn, *a):
         if it: best = max(best, fl.value/(e0.elapsed_time(e1)*1e-3))
     return best/1e12
 print('regs 8ch x 8w/SMSP', t('mc3b_fma_peak', 0, 20000))
-for v in (1,2,3,4):
+for v in (1,2,3,4,5,6):
     print('variant', v, t('mc3b_fma_peak_variant', v, 3000))

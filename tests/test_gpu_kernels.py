@@ -446,6 +446,36 @@ def test_sinusoid_grid_recurrence_accuracy(mc3):
         np.testing.assert_allclose(outs[4], outs[1], rtol=1e-11)
 
 
+def test_sinusoid_grid_with_data_and_weights(mc3):
+    """Same kernel with real data and uncertainties (the residual is formed as
+    y/sigma - d/sigma from a pre-scaled data tile): high S/N, offsets much
+    larger than the noise, steps on both sides of the pi/2 fold."""
+    import torch
+    from mc3_b200 import _lib
+    rs = np.random.RandomState(23)
+    dev = torch.device('cuda')
+    for n, span, snr in ((100000, 10.0, 10.0), (65536 + 77, 300.0, 1e4), (3001, 2.0, 1.0)):
+        nch = 160
+        x = np.linspace(0.1*span, 1.1*span, n)
+        truth = np.array([1.3, 0.37*span/10, 0.4, 25.0, 0.02])
+        unc = rs.uniform(0.5, 1.5, n)*truth[0]/snr
+        data = om.sinusoid(truth, x) + rs.normal(0, 1, n)*unc
+        P = truth + rs.normal(0, 1, (nch, 5))*np.array([0.05, 1e-4, 0.05, 0.05, 1e-3])/snr
+        if snr <= 10:      # a few samples per period (at S/N 1e4 the rounding of 2 pi x / p1
+            P[::7, 1] = rs.uniform(4, 12, P[::7].shape[0])*(x[1] - x[0])   # itself exceeds 1e-10)
+        dP, dx, dd, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+                          for a in (P, x, data, 1.0/unc))
+        ns = ctypes.c_int(0)
+        _lib.call('mc3b_model_chisq_plan', nch, n, _lib.F64, ctypes.byref(ns))
+        part = torch.empty((ns.value, nch), dtype=torch.float64, device=dev)
+        _lib.call('mc3b_model_chisq', 4, _lib.F64, dP.data_ptr(), 5, nch, 5,
+                  dx.data_ptr(), dd.data_ptr(), dw.data_ptr(), n, part.data_ptr(),
+                  nch, ns.value, _lib.stream_ptr())
+        got = part.sum(dim=0).cpu().numpy()
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/unc)**2) for p in P])
+        np.testing.assert_allclose(got, want, rtol=R64)
+
+
 def test_population_picks_grid_kernel_only_for_uniform_x(mc3):
     from mc3_b200.engine import Population
     p = pb.mcmc_case('sine')
