@@ -168,7 +168,7 @@ def run_reference(args):
         'chisq_evals_per_s': r['value']*100000,
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -264,10 +264,13 @@ def run_ours(args):
                 best = max(best, fl.value/(a.elapsed_time(b)*1e-3))
         achieved = flops/(kms*1e-3)
         prof = _profile_summary()
-        # FP64-pipe instructions per (chain, point) of the sinusoid kernel, read off
-        # the SASS (profiles/r1_model_chisq.md): 14 sine + 2 argument/line + 1 model
-        # + 3 residual/square = 20; each occupies the pipe like one FMA (2 flops).
-        pipe_instr = 9.0 if getattr(pop, 'grid', False) else 20.0   # uniform-grid recurrence: 4+2+3
+        # FP64-pipe instructions per (chain, point), read off the SASS: the plain
+        # sinusoid takes 14 sine + 2 argument/line + 1 model + 3 residual/square = 20,
+        # the uniform-grid recurrence 2 + 1 + 1 + 2 = 6 (profiles/r1_model_chisq.md);
+        # each occupies the pipe like one FMA (2 flops) -- or 1.5x that when it reads
+        # three fresh registers (profiles/r1_fp64_peak_probe.txt), which the peak
+        # probe's FMAs never do, so fp64_pipe_frac understates the pipe's busy time.
+        pipe_instr = 6.0 if getattr(pop, 'grid', False) else 20.0
         roof = {'bound': 'fp64' if args.dtype == 'f64' else 'fp32',
                 'kernel': 'k_model_chisq<SineGridModel>' if getattr(pop, 'grid', False) else 'k_model_chisq<SineModel>',
                 'fp64_pipe_instr_per_chain_point': pipe_instr,
@@ -349,7 +352,7 @@ def run_ours(args):
             'e2e': e2e, 'gpu_launches': launches, 'clocks': ck,
             'roofline': roof, 'cpu_baseline': cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         # Tearing NCCL down while captured graphs still reference the communicator
         # can block; everything is reported, so leave without running destructors.
@@ -357,6 +360,15 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         sys.stdout.flush()
         os._exit(0)
+
+
+_OUT = None
+
+
+def _emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def _profile_summary():
@@ -381,9 +393,15 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--dtype', default='f64', choices=['f64', 'f32'])
-    ap.add_argument('--cpu-steps', type=int, default=100)
+    ap.add_argument('--cpu-steps', type=int, default=2000)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything libraries print on fd 1 while
+    # the run lasts (NCCL's version banner, the hub's greeting) goes to stderr.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         run_reference(args)
     else:

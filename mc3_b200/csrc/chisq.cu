@@ -17,6 +17,8 @@
 //
 // Bound: FP64 (or FP32) pipe -- nchains*F flops per 24 bytes of data.
 #include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
 #include <type_traits>
 #include "models.cuh"
 
@@ -44,7 +46,10 @@ constexpr int RESIDENT = MC3B_RESIDENT;   // CTAs per SM the register budget is 
 template <typename T> struct tilecfg { static constexpr int TILE = MC3B_TILE_F64; };   // fp64: 128 beat 256 by 6% (finer balance)
 template <> struct tilecfg<float> { static constexpr int TILE = 512; };
 
+constexpr int SCHED_MAX = 384;      // splits a size schedule can describe (else equal splits)
 template <typename T> struct ChisqArgs {
+    int nsched;                     // > 0: split y covers tiles [tstart[y], tstart[y+1])
+    int32_t tstart[SCHED_MAX + 1];
     const double* params;
     int64_t ldp, nchains;
     const T *x, *d, *w;
@@ -86,7 +91,9 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
     // Tiles of this split: balanced contiguous ranges of FULL tiles; the
     // ragged tail (n % TILE points) belongs to the last split.
     const int64_t nfull = a.n / TILE;
-    const int64_t tb = nfull * blockIdx.y / gridDim.y, te = nfull * (blockIdx.y + 1) / gridDim.y;
+    int64_t tb, te;
+    if (a.nsched > 0) { tb = a.tstart[blockIdx.y]; te = a.tstart[blockIdx.y + 1]; }
+    else { tb = nfull * blockIdx.y / gridDim.y; te = nfull * (blockIdx.y + 1) / gridDim.y; }
     const int64_t nt = te - tb;
 
     if (a.use_tma) {
@@ -227,7 +234,10 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
 }
 
 // Shape policy (pure function of nchains, n, dtype).
-struct Shape { int lc, cpt, nsplit; int64_t groups; };
+struct Shape {
+    int lc, cpt, nsplit; int64_t groups;
+    int nsched; int32_t tstart[SCHED_MAX + 1];
+};
 
 Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     Shape s;
@@ -247,6 +257,32 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     if (ns > MC3B_MAX_SPLIT) ns = MC3B_MAX_SPLIT;
     if (ns < 1) ns = 1;
     s.nsplit = (int)ns;
+    s.nsched = 0;
+    // Decreasing split sizes ("factoring"): CTAs are dispatched in split order, so the
+    // last ones to start are short and the SMs run dry together.  Each batch of
+    // ~one wave of splits takes 1/f of the tiles that remain.
+    // f = 2, at least 4 tiles per split measured best at config 2 (0.203 -> 0.186 ms;
+    // profiles/r1_split_schedule.md); MC3B_SCHED="f,min" overrides, "0" gives equal splits.
+    double f = 2.0; int mn = 4;
+    if (const char* e = getenv("MC3B_SCHED")) { f = 0.0; sscanf(e, "%lf,%d", &f, &mn); }
+    if (mn < 1) mn = 1;
+    if (f >= 1.0 && s.lc == 32 && nfull < (1 << 30) && ns >= 8) {
+        const double rows = (double)sms * (s.cpt == 2 ? MC3B_RESIDENT2 : RESIDENT) / (double)s.groups;
+        const int per = (int)(rows + 0.999);
+        int64_t R = nfull; int k = 0; bool fits = true;
+        s.tstart[0] = 0;
+        while (R > 0 && fits) {
+            int64_t sz = (int64_t)((double)R / (f * rows) + 0.5);
+            if (sz < mn) sz = mn;
+            for (int j = 0; j < per && R > 0; j++) {
+                const int64_t t = sz < R ? sz : R;
+                if (k >= SCHED_MAX) { fits = false; break; }
+                s.tstart[k + 1] = (int32_t)(s.tstart[k] + t);
+                k++; R -= t;
+            }
+        }
+        if (fits && k >= 1) { s.nsched = k; s.nsplit = k; }
+    }
     return s;
 }
 
@@ -270,6 +306,8 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
     a.x = (const T*)x; a.d = (const T*)d; a.w = (const T*)w; a.n = n; a.partial = partial; a.ldpartial = ldpartial;
     a.use_tma = ((((uintptr_t)x | (uintptr_t)d | (uintptr_t)w) & 15) == 0) ? 1 : 0;
     Shape sh = plan_shape(nchains, n, dtype, mc3b_sm_count());
+    a.nsched = sh.nsched;
+    if (sh.nsched > 0) memcpy(a.tstart, sh.tstart, sizeof(int32_t) * (sh.nsched + 1));
     MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
     if (model_id == MC3B_MODEL_SINUSOID_GRID) {
         if constexpr (std::is_same<T, double>::value) {
