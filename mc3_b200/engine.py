@@ -408,7 +408,7 @@ class Population:
             _lib.call('mc3b_init_trials', ctypes.byref(self.S), kick, nt, rnd,
                       trial.data_ptr(), ok.data_ptr(), _lib.stream_ptr())
             self.launches += 1
-            lp = -0.5*self.chisq(trial)
+            lp = self._trial_log_post(trial)
             good = (ok != 0) & torch.isfinite(lp)
             idx = torch.nonzero(good).flatten()[:M0 - got]
             rows.append(trial[idx])
@@ -424,6 +424,24 @@ class Population:
                 'non-finite values.')
         full = torch.cat(rows)
         self.set_initial(full[:, self.d_ifree.long()], torch.cat(lps))
+
+    def _trial_log_post(self, trial):
+        """log-posterior of the initial-population trials.  With the chains
+        partitioned over devices each device evaluates a contiguous block of the
+        rows and the blocks are all-gathered (the trials themselves are Philox
+        draws every device generates identically)."""
+        nt = trial.shape[0]
+        if self.world == 1 or self.shard != 'chains':
+            return -0.5*self.chisq(trial)
+        per = -(-nt//self.world)
+        buf = torch.full((self.world*per, 1), float('nan'), dtype=torch.float64,
+                         device=self.dev)
+        lo = min(self.rank*per, nt)
+        hi = min(lo + per, nt)
+        if hi > lo:
+            buf[self.rank*per:self.rank*per + (hi - lo), 0] = -0.5*self.chisq(trial[lo:hi])
+        allgather_rows(buf, self.rank*per, per, self.group)
+        return buf[:nt, 0].contiguous()
 
     def set_initial(self, Z0, log_post0):
         """Install M0 initial history rows and start every chain from row c
@@ -492,12 +510,22 @@ class Population:
                                self.nlocal, self.group)
 
     def _capture(self, ngens):
-        """CUDA graph of `ngens` device-driven generations."""
+        """CUDA graph of `ngens` device-driven generations.  Captured on a side
+        stream with capture_begin/capture_end directly: torch.cuda.graph()'s
+        gc.collect + empty_cache cost ~10 ms, a fifth of a 200-generation run."""
         g = torch.cuda.CUDAGraph()
         before = self.launches
-        with torch.cuda.graph(g):
-            for _ in range(ngens):
-                self._generation(-1)
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                for _ in range(ngens):
+                    self._generation(-1)
+            finally:
+                g.capture_end()
+        cur.wait_stream(side)
         per = self.launches - before
         self.launches = before
         return g, per
@@ -511,7 +539,9 @@ class Population:
         if use_graph is None:
             # A generation with >= ~0.3 ms of device work hides its three host
             # launches completely: skip the capture (10-15 ms) and run eagerly.
-            heavy = float(self.nlocal)*self.ndata > 2e8 and not self.small
+            # (single device only: an eager NCCL all-gather per generation costs the
+            # host more than the generation itself, 0.69 vs 0.24 ms at 8 GPUs)
+            heavy = float(self.nlocal)*self.ndata > 2e8 and not self.small and self.world == 1
             use_graph = self.kind == 'builtin' and not heavy and not \
                 (self.world > 1 and self.shard == 'chains' and self.sampler == 'snooker'
                  and self.p2p is None)
