@@ -57,6 +57,15 @@ int mc3b_device_sms(void);
  * Deterministic function of its arguments. */
 int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit);
 
+/* The split boundaries behind that plan, in data points: split s sums the points
+ * [point_start[s], point_start[s+1]); point_start has nsplit+1 entries (HOST
+ * memory, `cap` >= nsplit+1) and ends at n.  Large populations get splits of
+ * decreasing size: CTAs start in split order, so the last to start are short and
+ * the SMs finish together.  (No reference counterpart: the reference sums one
+ * chain at a time, _chisq.c:111-140.) */
+int mc3b_model_chisq_splits(int64_t nchains, int64_t n, int dtype,
+                            int64_t* point_start, int cap, int* nsplit);
+
 /* Fused built-in model + data chi-squared, batched over chains:
  *   partial[s, c] = sum over the points i of split s of
  *                   ((model(params[c], x_i) - data_i) * invsig_i)^2

@@ -400,6 +400,23 @@ extern "C" int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int*
     return MC3B_OK;
 }
 
+extern "C" int mc3b_model_chisq_splits(int64_t nchains, int64_t n, int dtype, int64_t* point_start, int cap,
+                                       int* nsplit) {
+    MC3B_CHECK_ARG(nchains > 0 && n > 0 && nsplit != nullptr && point_start != nullptr, "bad plan arguments");
+    MC3B_CHECK_ARG(dtype == MC3B_F64 || dtype == MC3B_F32, "bad dtype %d", dtype);
+    int sms = mc3b_sm_count();
+    if (sms <= 0) sms = 148;
+    const Shape sh = plan_shape(nchains, n, dtype, sms);
+    MC3B_CHECK_ARG(cap >= sh.nsplit + 1, "point_start holds %d entries, the plan needs %d", cap, sh.nsplit + 1);
+    const int64_t tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
+    const int64_t nfull = n / tile;
+    for (int y = 0; y <= sh.nsplit; y++)
+        point_start[y] = tile * (sh.nsched > 0 ? (int64_t)sh.tstart[y] : nfull * y / sh.nsplit);
+    point_start[sh.nsplit] = n;                       // the ragged tail belongs to the last split
+    *nsplit = sh.nsplit;
+    return MC3B_OK;
+}
+
 extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,
                                 int nmodel, const void* x, const void* data, const void* invsig, int64_t n,
                                 double* partial, int64_t ldpartial, int nsplit, void* stream) {

@@ -20,7 +20,7 @@ for spec in sys.argv[1:]:
     if r.returncode:
         sys.stderr.write(r.stderr); raise SystemExit(1)
     for ln in r.stderr.splitlines():
-        if 'SineGridModelPM' in ln and 'Compiling' in ln:
+        if 'SineGridModeldLi32ELi1' in ln and 'Compiling' in ln:
             grab = 3
         if 'grab' in dir() and grab > 0 and ('Used' in ln or 'spill' in ln):
             print(name, ln.strip()); grab -= 1

@@ -48,6 +48,44 @@ def test_version_and_plan_without_device():
     assert ns.value == ns2.value            # deterministic shape policy
 
 
+@pytest.mark.parametrize('nchains,n', [(4096, 100000), (4096, 100001), (1024, 100000), (128, 100000),
+                                       (65536, 1000000), (8192, 10**7), (96, 5000), (7, 100),
+                                       (4096, 127), (2048, 1 << 20)])
+def test_split_boundaries_cover_the_series(nchains, n):
+    """The (possibly decreasing-size) data splits of the model kernel partition
+    [0, n): contiguous, whole tiles except the tail, sizes never growing."""
+    import ctypes
+    import numpy as np
+    ns = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_plan', nchains, n, _lib.F64, ctypes.byref(ns))
+    cap = ns.value + 1
+    buf = (ctypes.c_int64*cap)()
+    ns2 = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_splits', nchains, n, _lib.F64, buf, cap, ctypes.byref(ns2))
+    assert ns2.value == ns.value
+    b = np.array(buf[:cap])
+    assert b[0] == 0 and b[-1] == n
+    assert np.all(np.diff(b) >= 0)
+    assert np.all(b[:-1] % 128 == 0)                 # fp64 tiles of 128 points
+    if ns.value > 1:
+        sizes = np.diff(b)[:-1]//128                 # all but the tail-carrying last split
+        if sizes.size > 1 and n >= 128*ns.value:
+            assert np.all(np.diff(sizes[:-1]) <= 1)  # equal (+-1) or decreasing
+    with pytest.raises(_lib.Mc3bError, match='entries'):
+        _lib.call('mc3b_model_chisq_splits', nchains, n, _lib.F64, buf, ns.value, ctypes.byref(ns2))
+
+
+def test_large_population_gets_decreasing_splits():
+    import ctypes
+    import numpy as np
+    buf = (ctypes.c_int64*512)()
+    ns = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_splits', 4096, 100000, _lib.F64, buf, 512, ctypes.byref(ns))
+    sizes = np.diff(np.array(buf[:ns.value + 1]))//128
+    assert sizes[0] >= 3*sizes[-2] and sizes[:-1].min() >= 4     # factoring, at least 4 tiles
+    assert sizes[:-1].sum() + sizes[-1] == 100000//128
+
+
 def test_bad_arguments_raise():
     import ctypes
     ns = ctypes.c_int(0)
