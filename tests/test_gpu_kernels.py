@@ -476,6 +476,41 @@ def test_sinusoid_grid_with_data_and_weights(mc3):
         np.testing.assert_allclose(got, want, rtol=R64)
 
 
+@pytest.mark.parametrize('model_id,nch,n', [(4, 4096, 100000), (1, 4096, 100000 + 37),
+                                            (0, 1024, 60000), (4, 512, 20011)])
+def test_partial_rows_are_the_oracle_over_their_split(mc3, model_id, nch, n):
+    """Every row of the partial workspace is the chi-squared over the data range
+    mc3b_model_chisq_splits reports for it (decreasing split sizes included)."""
+    from mc3_b200 import _lib
+    rs = np.random.RandomState(model_id + n)
+    dev = torch.device('cuda')
+    x = np.linspace(0.0, 10.0, n)
+    if model_id == 0:
+        P = rs.normal(0, 1, (nch, 3))
+        f, nm, npar = om.quad, 3, 3
+    else:
+        P = np.column_stack([rs.uniform(0.5, 2, nch), rs.uniform(0.3, 3.0, nch), rs.uniform(-3, 3, nch),
+                             rs.uniform(-1, 1, nch), rs.uniform(-0.1, 0.1, nch)])
+        f, nm, npar = om.sinusoid, 5, 5
+    unc = rs.uniform(0.5, 1.5, n)
+    data = f(P[0], x) + rs.normal(0, 1, n)*unc
+    dP, dx, dd, dw = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (P, x, data, 1.0/unc))
+    ns = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_plan', nch, n, _lib.F64, ctypes.byref(ns))
+    bounds = (ctypes.c_int64*(ns.value + 1))()
+    _lib.call('mc3b_model_chisq_splits', nch, n, _lib.F64, bounds, ns.value + 1, ctypes.byref(ns))
+    b = np.array(bounds[:ns.value + 1])
+    part = torch.empty((ns.value, nch), dtype=torch.float64, device=dev)
+    _lib.call('mc3b_model_chisq', model_id, _lib.F64, dP.data_ptr(), npar, nch, nm, dx.data_ptr(),
+              dd.data_ptr(), dw.data_ptr(), n, part.data_ptr(), nch, ns.value, _lib.stream_ptr())
+    got = part.cpu().numpy()
+    for c in (0, 1, nch//2, nch - 1):
+        r2 = ((f(P[c], x) - data)/unc)**2
+        want = np.array([r2[b[s]:b[s + 1]].sum() for s in range(ns.value)])
+        np.testing.assert_allclose(got[:, c], want, rtol=1e-9, atol=1e-9*want.max())
+        np.testing.assert_allclose(got[:, c].sum(), r2.sum(), rtol=R64)
+
+
 def test_population_picks_grid_kernel_only_for_uniform_x(mc3):
     from mc3_b200.engine import Population
     p = pb.mcmc_case('sine')
