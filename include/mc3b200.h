@@ -35,7 +35,7 @@ enum { MC3B_F64 = 0, MC3B_F32 = 1 };
 enum { MC3B_MODEL_POLYNOMIAL = 0, MC3B_MODEL_SINUSOID = 1,
        MC3B_MODEL_GAUSSIAN = 2, MC3B_MODEL_BOX = 3,
        /* sinusoid on a UNIFORM abscissa grid (caller's assertion: x[i] = x[0] + i dx to
-        * a few ulp): same values to ~3e-14 of the amplitude; the sine advances by a
+        * a few ulp): same values to 2e-15 (8e-14 for steps of radians per sample) of the amplitude; the sine advances by a
         * three-term recurrence re-anchored per tile (models.cuh SineGridModel) */
        MC3B_MODEL_SINUSOID_GRID = 4 };
 enum { MC3B_MRW = 0, MC3B_DEMC = 1, MC3B_SNOOKER = 2 };

@@ -214,7 +214,8 @@ template <> struct SineModel<double> {
 //
 // Accuracy: every tile restarts the sequences (three one-step rotations from the
 // tile's first point), so rounding accumulates over TILE/4 = 32 steps: an error e
-// made m steps earlier shows as e sin((m+1)D)/sin D, < 3e-14 A in total unless D
+// made m steps earlier shows as e sin((m+1)D)/sin D: <= 2e-15 A for k dx < 0.01,
+// <= 8e-14 A up to 2.5 rad per sample (profiles/recurrence_error.py) unless D
 // is within ~0.14 rad of pi (period ~ 8 samples, 1e-13); such chains, and model
 // arguments beyond 1e9, are flagged and take the direct evaluation (GUARD).
 // The tile's first point itself comes from fast_sincos_core every 8th tile and
