@@ -309,9 +309,11 @@ def run_ours(args):
         # each occupies the pipe like one FMA (2 flops) -- or 1.5x that when it reads
         # three fresh registers (profiles/r1_fp64_peak_probe.txt), which the peak
         # probe's FMAs never do, so fp64_pipe_frac understates the pipe's busy time.
-        pipe_instr = 6.0 if getattr(pop, 'grid', False) else 20.0
+        pipe_instr = 6.0 if getattr(pop, 'grid', False) else (19.0 if pop.usig else 20.0)
+        kname = ('k_sinegrid<USIG=%s>' % ('true' if pop.usig else 'false')) \
+            if getattr(pop, 'grid', False) else 'k_model_chisq<SineModel>'
         roof = {'bound': 'fp64' if args.dtype == 'f64' else 'fp32',
-                'kernel': 'k_model_chisq<SineGridModel>' if getattr(pop, 'grid', False) else 'k_model_chisq<SineModel>',
+                'kernel': kname,
                 'fp64_pipe_instr_per_chain_point': pipe_instr,
                 'achieved': achieved/1e12, 'peak': best/1e12, 'unit': 'TFLOP/s',
                 'frac': achieved/best, 'traffic': prof.get('dram_bytes_per_launch'),

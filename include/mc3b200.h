@@ -83,6 +83,41 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
                      double* partial, int64_t ldpartial, int nsplit,
                      void* stream);
 
+/* Options of mc3b_model_chisq_ex ([host] struct; NULL or all-zero = mc3b_model_chisq).
+ *
+ * plan_chains    chain count the launch shape is planned for (0 = nchains).  The bits
+ *                of a chain's chi-squared depend on the order its terms are added,
+ *                i.e. on the split boundaries = f(plan_chains, n, dtype, SM count), not
+ *                on which or how many chains the launch holds: plan once for the whole
+ *                population (mc3b_model_chisq_plan(plan_chains, ...)) and any subset of
+ *                its chains, on any device of the same type, gets identical bits.
+ * uniform_sigma  all uncertainties are equal: invsig points to ONE value; residuals are
+ *                plain differences and the sums are scaled by invsig[0]^2 (no weight
+ *                stream).  For MC3B_MODEL_SINUSOID_GRID the abscissa is not streamed
+ *                either (x[0] and x[n-1] define the grid).
+ * fuse           non-NULL: the last CTA to finish a group of chains adds their partial
+ *                rows (split order) plus priors and takes their Metropolis step, exactly
+ *                as mc3b_metropolis(fuse, partial, ldpartial, nsplit, c_off, gen, zrow0,
+ *                c_off, c_off + nchains) would -- without the second launch.  fuse_done:
+ *                device int32[groups + 1] (groups <= nchains/32 + 1), zero before the
+ *                first use, left zero by every launch.  advance: the last group also
+ *                increments *fuse->gen_dev (replaces mc3b_advance). */
+struct mc3b_sampler;
+typedef struct mc3b_chisq_opts {
+    int64_t plan_chains;
+    int32_t uniform_sigma;
+    int32_t advance;
+    const struct mc3b_sampler* fuse;
+    int32_t* fuse_done;
+    int64_t c_off, gen, zrow0;
+} mc3b_chisq_opts_t;
+
+int mc3b_model_chisq_ex(int model_id, int dtype, const double* params, int64_t ldp,
+                        int64_t nchains, int nmodel, const void* x,
+                        const void* data, const void* invsig, int64_t n,
+                        double* partial, int64_t ldpartial, int nsplit,
+                        const mc3b_chisq_opts_t* opts, void* stream);
+
 /* model[c, i] = model(params[c], x_i), fp64, out is [nchains, n] row-major. */
 int mc3b_model_eval(int model_id, const double* params, int64_t ldp,
                     int64_t nchains, int nmodel, const double* x, int64_t n,
@@ -204,6 +239,15 @@ int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial,
                     int64_t ldpartial, int nsplit, int64_t c_off, int64_t gen,
                     int64_t zrow0, int64_t c_begin, int64_t c_end, void* stream);
 
+/* Report-point counters of this device's chains, packed for one D2H copy
+ * (replaces the hub's reads of the shared numaccept / outbounds / bestp arrays,
+ * mcmc_driver.py:302-320): out[0] = accepted proposals summed over the device's
+ * chains, out[1] = lowest accepted chi-squared (inf if none), out[2], out[3] = the
+ * generation and chain where it was reached first (-1 if none), out[4 .. 4+nfree) =
+ * its free parameters, out[4+nfree .. 4+2 nfree) = the out-of-bounds counters.
+ * out: 4 + 2 nfree doubles.  [host] s. */
+int mc3b_pack_counters(const mc3b_sampler_t* s, double* out, void* stream);
+
 /* Small populations (<= 256 chains, one device, built-in model, data chi-squared):
  * run generations gen0 .. gen0+ngen-1 inside ONE resident CTA -- proposal,
  * model + chi-squared (a warp per chain), Metropolis step and history write per
@@ -242,6 +286,19 @@ int mc3b_gelman_rubin(const double* Z, int64_t nfree, int64_t nchains,
                       int64_t M0, const int64_t* rows, int64_t ldr,
                       int64_t burnin, int64_t niter, double* work, double* psrf,
                       void* stream);
+
+/* The two stages of mc3b_gelman_rubin, for chains spread over devices: every
+ * device fills work[0, c, :] (mean) and work[1, c, :] (population variance,
+ * gelman.py:75-76) for ITS chains [c_begin, c_end) from its own history rows; the
+ * caller all-gathers the two [nchains, nfree] blocks (2 nchains nfree doubles -- not
+ * the history) and every device evaluates W, B, V, sqrt(V/W) over all chains in chain
+ * order (gelman.py:77-92): identical bits to the one-device call. */
+int mc3b_gelman_rubin_moments(const double* Z, int64_t nfree, int64_t nchains,
+                              int64_t M0, const int64_t* rows, int64_t ldr,
+                              int64_t burnin, int64_t niter, int64_t c_begin,
+                              int64_t c_end, double* work, void* stream);
+int mc3b_gelman_rubin_psrf(const double* work, int64_t nfree, int64_t nchains,
+                           int64_t niter, double* psrf, void* stream);
 
 /* ------------------------------------------------------------------------
  * Wavelet likelihood   (replaces _dwt.c + wavelet.h)

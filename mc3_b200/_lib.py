@@ -41,6 +41,13 @@ class SamplerStruct(ctypes.Structure):
     ]
 
 
+class ChisqOpts(ctypes.Structure):
+    """mc3b_chisq_opts_t."""
+    _fields_ = [('plan_chains', c_i64), ('uniform_sigma', c_i32), ('advance', c_i32),
+                ('fuse', ctypes.POINTER(SamplerStruct)), ('fuse_done', c_vp),
+                ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64)]
+
+
 class DrawsStruct(ctypes.Structure):
     """mc3b_draws_t."""
     _fields_ = [('normal', c_vp), ('a', c_vp), ('b', c_vp), ('iz', c_vp),
@@ -57,6 +64,9 @@ _SIGS = {
                                         ctypes.POINTER(c_int)]),
     'mc3b_model_chisq': (c_int, [c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp,
                                  c_vp, c_vp, c_i64, c_vp, c_i64, c_int, c_vp]),
+    'mc3b_model_chisq_ex': (c_int, [c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp,
+                                    c_vp, c_vp, c_i64, c_vp, c_i64, c_int,
+                                    ctypes.POINTER(ChisqOpts), c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),
     'mc3b_chisq_finish': (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,
@@ -70,6 +80,7 @@ _SIGS = {
                                     ctypes.POINTER(DrawsStruct), c_i64, c_i64, c_vp]),
     'mc3b_metropolis': (c_int, [ctypes.POINTER(SamplerStruct), c_vp, c_i64, c_int,
                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    'mc3b_pack_counters': (c_int, [ctypes.POINTER(SamplerStruct), c_vp, c_vp]),
     'mc3b_advance': (c_int, [ctypes.POINTER(SamplerStruct), c_vp]),
     'mc3b_run_small': (c_int, [ctypes.POINTER(SamplerStruct), c_int, c_int, c_vp, c_vp, c_vp,
                                c_i64, c_i64, c_i64, c_vp]),
@@ -79,6 +90,9 @@ _SIGS = {
                                c_vp, c_vp]),
     'mc3b_gelman_rubin': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
                                   c_i64, c_vp, c_vp, c_vp]),
+    'mc3b_gelman_rubin_moments': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64,
+                                          c_i64, c_i64, c_i64, c_vp, c_vp]),
+    'mc3b_gelman_rubin_psrf': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     'mc3b_dwt_workspace': (c_i64, [c_i64, c_i64]),
     'mc3b_dwt_chisq': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp,
                                c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmc3b200.so')
-SOURCES = ['runtime.cu', 'chisq.cu', 'sampler.cu', 'small.cu', 'dwt.cu', 'timeavg.cu']
+SOURCES = ['runtime.cu', 'chisq.cu', 'chisq_grid.cu', 'sampler.cu', 'small.cu', 'dwt.cu', 'timeavg.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
     '-std=c++17', '-Xcompiler', '-fPIC', '--fmad=true',
@@ -43,19 +43,23 @@ def build(force=False, verbose=False):
     objs = []
     logs = []
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    jobs = []
     for src in srcs:
         path = os.path.join(CSRC, src)
         obj = os.path.join(CSRC, src[:-3] + '.o')
         objs.append(obj)
         if force or _stale(obj, [path] + headers):
             cmd = [nvcc] + NVCC_FLAGS + ['-c', path, '-o', obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
-            logs.append(r.stderr)
-            if r.returncode != 0:
-                sys.stderr.write(r.stdout + r.stderr)
-                raise RuntimeError(f'nvcc failed on {src}')
-            if verbose:
-                sys.stderr.write(r.stderr)
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE,
+                                               stderr=subprocess.PIPE, text=True)))
+    for src, pr in jobs:                       # the translation units compile side by side
+        out, err = pr.communicate()
+        logs.append(err)
+        if pr.returncode != 0:
+            sys.stderr.write(out + err)
+            raise RuntimeError(f'nvcc failed on {src}')
+        if verbose:
+            sys.stderr.write(err)
     if force or _stale(LIB, objs):
         cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,45 +21,16 @@
 #include <stdio.h>
 #include <type_traits>
 #include "models.cuh"
+#include "sampler_dev.cuh"
+
+#include "chisq_args.cuh"
 
 namespace {
 
-#ifndef MC3B_WARPS
-#define MC3B_WARPS 4
-#endif
-#ifndef MC3B_RESIDENT
-#define MC3B_RESIDENT 6
-#endif
-#ifndef MC3B_RESIDENT2
-#define MC3B_RESIDENT2 4
-#endif
-#ifndef MC3B_LOOP_UNROLL
-#define MC3B_LOOP_UNROLL 2
-#endif
-#ifndef MC3B_TILE_F64
-#define MC3B_TILE_F64 128
-#endif
-constexpr int WARPS = MC3B_WARPS;
-constexpr int STAGES = 3;
-constexpr int LOOP_UNROLL = MC3B_LOOP_UNROLL;   // point groups of the inner loop unrolled together
-constexpr int RESIDENT = MC3B_RESIDENT;   // CTAs per SM the register budget is tuned for (ILP over occupancy)
-template <typename T> struct tilecfg { static constexpr int TILE = MC3B_TILE_F64; };   // fp64: 128 beat 256 by 6% (finer balance)
-template <> struct tilecfg<float> { static constexpr int TILE = 512; };
-
-constexpr int SCHED_MAX = 384;      // splits a size schedule can describe (else equal splits)
-template <typename T> struct ChisqArgs {
-    int nsched;                     // > 0: split y covers tiles [tstart[y], tstart[y+1])
-    int32_t tstart[SCHED_MAX + 1];
-    const double* params;
-    int64_t ldp, nchains;
-    const T *x, *d, *w;
-    int64_t n;
-    double* partial;
-    int64_t ldpartial;
-    int use_tma;
-};
-
-template <class M, typename T, int LC, int CPT>
+// USIG: one uncertainty for all points (w[0]): residuals are plain differences
+// (a two-register DADD instead of a multiply or a three-register FMA) and the sum
+// is scaled by w[0]^2 once per partial.
+template <class M, typename T, int LC, int CPT, bool USIG>
 __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESIDENT)) k_model_chisq(ChisqArgs<T> a) {
     constexpr int TILE = tilecfg<T>::TILE;
     constexpr int LP = 32 / LC;
@@ -104,20 +75,23 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
         __syncthreads();
         auto issue = [&](int64_t t, int s) {
             const int64_t off = t * TILE;
-            mbar_expect_tx(&bar[s], 3u * TILE * sizeof(T));
+            mbar_expect_tx(&bar[s], (USIG ? 2u : 3u) * TILE * sizeof(T));
             bulk_g2s(sx[s], a.x + off, TILE * sizeof(T), &bar[s]);
             bulk_g2s(sd[s], a.d + off, TILE * sizeof(T), &bar[s]);
-            bulk_g2s(sw[s], a.w + off, TILE * sizeof(T), &bar[s]);
+            if constexpr (!USIG) bulk_g2s(sw[s], a.w + off, TILE * sizeof(T), &bar[s]);
         };
         if (threadIdx.x == 0)
             for (int s = 0; s < STAGES && s < nt; s++) issue(tb + s, s);
-        constexpr bool PM = premul_of<M>::value;
+        constexpr bool PM = premul_of<M>::value && !USIG;
+        // PM keeps d/sigma in a buffer of its own: TMA never writes it, so no generic-proxy
+        // store ever meets an async-proxy refill of the same bytes (no proxy fence needed)
+        __shared__ __align__(128) T sdw[PM ? STAGES : 1][PM ? TILE : 2];
         // PM: data tile <- data / sigma, once for all chains of the CTA.  Tile it+1 is
         // scaled at the end of tile it, so that the stage-release barrier publishes it.
         auto premul = [&](int64_t t) {
             const int s1 = (int)(t % STAGES);
             mbar_wait(&bar[s1], (uint32_t)((t / STAGES) & 1));
-            for (int i = threadIdx.x; i < TILE; i += WARPS * 32) sd[s1][i] *= sw[s1][i];
+            for (int i = threadIdx.x; i < TILE; i += WARPS * 32) sdw[PM ? s1 : 0][PM ? i : 0] = sd[s1][i] * sw[s1][i];
         };
         if constexpr (PM) {
             if (nt > 0) premul(0);
@@ -149,8 +123,9 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
                     eval_points<M, T, U>(mdl[k], x, y, 0);
 #pragma unroll
                     for (int u = 0; u < U; u++) {
-                        const T r = PM ? fma(y[u], sw[s][i + u * LP], -sd[s][i + u * LP])
-                                       : (y[u] - sd[s][i + u * LP]) * sw[s][i + u * LP];
+                        const T r = USIG ? y[u] - sd[s][i + u * LP]
+                                    : PM ? fma(y[u], sw[s][i + u * LP], -sdw[PM ? s : 0][PM ? i + u * LP : 0])
+                                         : (y[u] - sd[s][i + u * LP]) * sw[s][i + u * LP];
                         uacc[k][u] = fma(r, r, uacc[k][u]);
                     }
                 }
@@ -164,8 +139,9 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
                         mdl[k].clear();
                         tacc[k] = (T)0;
                         for (int i = lp; i < TILE; i += LP) {
-                            const T r = PM ? fma(mdl[k].eval_safe(sx[s][i]), sw[s][i], -sd[s][i])
-                                           : (mdl[k].eval_safe(sx[s][i]) - sd[s][i]) * sw[s][i];
+                            const T r = USIG ? mdl[k].eval_safe(sx[s][i]) - sd[s][i]
+                                        : PM ? fma(mdl[k].eval_safe(sx[s][i]), sw[s][i], -sdw[PM ? s : 0][PM ? i : 0])
+                                             : (mdl[k].eval_safe(sx[s][i]) - sd[s][i]) * sw[s][i];
                             tacc[k] = fma(r, r, tacc[k]);
                         }
                     }
@@ -177,17 +153,14 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
                 if (it + 1 < nt) premul(it + 1);
             }
             __syncthreads();                    // everyone is done reading stage s
-            if (threadIdx.x == 0 && it + STAGES < nt) {
-                if constexpr (PM) fence_proxy_async();
-                issue(tb + it + STAGES, s);
-            }
+            if (threadIdx.x == 0 && it + STAGES < nt) issue(tb + it + STAGES, s);
         }
     } else {
         for (int64_t it = 0; it < nt; it++) {   // unaligned inputs: plain staged loads
             const int64_t off = (tb + it) * TILE;
             __syncthreads();
             for (int i = threadIdx.x; i < TILE; i += WARPS * 32) {
-                sx[0][i] = a.x[off + i]; sd[0][i] = a.d[off + i]; sw[0][i] = a.w[off + i];
+                sx[0][i] = a.x[off + i]; sd[0][i] = a.d[off + i]; sw[0][i] = USIG ? (T)1 : a.w[off + i];
             }
             __syncthreads();
             T tacc[CPT];
@@ -212,7 +185,7 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
 #pragma unroll
         for (int k = 0; k < CPT; k++) tacc[k] = (T)0;
         for (int64_t i = nfull * TILE + lp; i < a.n; i += LP) {
-            const T x = a.x[i], d = a.d[i], w = a.w[i];
+            const T x = a.x[i], d = a.d[i], w = USIG ? (T)1 : a.w[i];
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
                 const T r = (mdl[k].eval_safe(x) - d) * w;
@@ -223,35 +196,43 @@ __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESID
         for (int k = 0; k < CPT; k++) acc[k] += (double)tacc[k];
     }
 
+    double w2 = 1.0;
+    if constexpr (USIG) { const double w0 = (double)a.w[0]; w2 = w0 * w0; }
 #pragma unroll
     for (int k = 0; k < CPT; k++) {
         double v = acc[k];
 #pragma unroll
         for (int o = 16; o >= LC; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         const int64_t c = cbase + (int64_t)k * LC;
-        if (lp == 0 && c < a.nchains) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = v;
+        if (lp == 0 && c < a.nchains) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = USIG ? v * w2 : v;
     }
+    if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * LC * CPT);
 }
 
-// Shape policy (pure function of nchains, n, dtype).
+// Shape policy: a pure function of (plan_chains, n, dtype, SM count).  plan_chains
+// is the chain count the shape is planned FOR -- by default the chains of the
+// launch; a caller that wants identical chi-squared bits however the chains are
+// spread over launches or devices plans for the whole population and launches any
+// subset of it with that plan (the split boundaries, hence the order in which a
+// chain's terms are added, then do not depend on the subset).
 struct Shape {
-    int lc, cpt, nsplit; int64_t groups;
+    int lc, nsplit;
     int nsched; int32_t tstart[SCHED_MAX + 1];
 };
 
 Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     Shape s;
+    int RESIDENT = mc3b_chisq::RESIDENT;            // MC3B_PLAN_RESIDENT: experiments with other residencies
+    if (const char* e = getenv("MC3B_PLAN_RESIDENT")) RESIDENT = atoi(e) > 0 ? atoi(e) : RESIDENT;
     s.lc = nchains >= 96 ? 32 : (nchains >= 12 ? 8 : 1);
-    s.cpt = 1;      // two chains per lane (MC3B_CPT=2) measured slower on B200: registers > tile-read savings
-    if (const char* e = getenv("MC3B_CPT")) s.cpt = (s.lc == 32 && atoi(e) == 2) ? 2 : 1;
     const int tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
-    s.groups = ceil_div64(nchains, (int64_t)WARPS * s.lc * s.cpt);
+    const int64_t groups = ceil_div64(nchains, (int64_t)WARPS * s.lc);
     const int64_t nfull = n / tile;
     int waves = 2;
     if (const char* e = getenv("MC3B_WAVES")) waves = atoi(e) > 0 ? atoi(e) : 1;
     // whole waves of RESIDENT CTAs per SM (round to nearest: a few CTAs over one
     // wave cost a whole extra wave, so round down unless clearly closer to the next)
-    int64_t want = ((int64_t)sms * (s.cpt == 2 ? MC3B_RESIDENT2 : RESIDENT) * waves) / s.groups;
+    int64_t want = ((int64_t)sms * RESIDENT * waves) / groups;
     int64_t ns = want < 1 ? 1 : want;
     if (ns > nfull) ns = nfull;
     if (ns > MC3B_MAX_SPLIT) ns = MC3B_MAX_SPLIT;
@@ -267,7 +248,7 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     if (const char* e = getenv("MC3B_SCHED")) { f = 0.0; sscanf(e, "%lf,%d", &f, &mn); }
     if (mn < 1) mn = 1;
     if (f >= 1.0 && s.lc == 32 && nfull < (1 << 30) && ns >= 8) {
-        const double rows = (double)sms * (s.cpt == 2 ? MC3B_RESIDENT2 : RESIDENT) / (double)s.groups;
+        const double rows = (double)sms * RESIDENT / (double)groups;
         const int per = (int)(rows + 0.999);
         int64_t R = nfull; int k = 0; bool fits = true;
         s.tstart[0] = 0;
@@ -286,13 +267,12 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     return s;
 }
 
-template <class M, typename T>
-int launch_model_chisq(const Shape& sh, ChisqArgs<T> a, int nsplit, cudaStream_t st) {
-    dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
-    if (sh.lc == 32 && sh.cpt == 2) k_model_chisq<M, T, 32, 2><<<grid, block, 0, st>>>(a);
-    else if (sh.lc == 32) k_model_chisq<M, T, 32, 1><<<grid, block, 0, st>>>(a);
-    else if (sh.lc == 8) k_model_chisq<M, T, 8, 1><<<grid, block, 0, st>>>(a);
-    else k_model_chisq<M, T, 1, 1><<<grid, block, 0, st>>>(a);
+template <class M, typename T, bool USIG>
+int launch_model_chisq(const Shape& sh, const ChisqArgs<T>& a, dim3 grid, cudaStream_t st) {
+    dim3 block(WARPS * 32);
+    if (sh.lc == 32) k_model_chisq<M, T, 32, 1, USIG><<<grid, block, 0, st>>>(a);
+    else if (sh.lc == 8) k_model_chisq<M, T, 8, 1, USIG><<<grid, block, 0, st>>>(a);
+    else k_model_chisq<M, T, 1, 1, USIG><<<grid, block, 0, st>>>(a);
     MC3B_CHECK_LAUNCH("k_model_chisq");
     return MC3B_OK;
 }
@@ -300,28 +280,49 @@ int launch_model_chisq(const Shape& sh, ChisqArgs<T> a, int nsplit, cudaStream_t
 template <typename T>
 int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchains, int nmodel,
                   const void* x, const void* d, const void* w, int64_t n, double* partial, int64_t ldpartial,
-                  int nsplit, int dtype, cudaStream_t st) {
-    ChisqArgs<T> a;
-    a.params = params; a.ldp = ldp; a.nchains = nchains;
-    a.x = (const T*)x; a.d = (const T*)d; a.w = (const T*)w; a.n = n; a.partial = partial; a.ldpartial = ldpartial;
-    a.use_tma = ((((uintptr_t)x | (uintptr_t)d | (uintptr_t)w) & 15) == 0) ? 1 : 0;
-    Shape sh = plan_shape(nchains, n, dtype, mc3b_sm_count());
-    a.nsched = sh.nsched;
-    if (sh.nsched > 0) memcpy(a.tstart, sh.tstart, sizeof(int32_t) * (sh.nsched + 1));
+                  int nsplit, int dtype, const mc3b_chisq_opts_t& o, cudaStream_t st) {
+    ChisqArgs<T> A;
+    A.params = params; A.ldp = ldp; A.nchains = nchains;
+    A.x = (const T*)x; A.d = (const T*)d; A.w = (const T*)w; A.n = n; A.partial = partial; A.ldpartial = ldpartial;
+    const bool usig = o.uniform_sigma != 0;
+    A.use_tma = ((((uintptr_t)x | (uintptr_t)d | (usig ? 0 : (uintptr_t)w)) & 15) == 0) ? 1 : 0;
+    const int64_t plan_chains = o.plan_chains > 0 ? o.plan_chains : nchains;
+    MC3B_CHECK_ARG(plan_chains >= nchains, "plan_chains (%lld) is smaller than the launch (%lld chains)",
+                   (long long)plan_chains, (long long)nchains);
+    const Shape sh = plan_shape(plan_chains, n, dtype, mc3b_sm_count());
+    A.nsched = sh.nsched;
+    if (sh.nsched > 0) memcpy(A.tstart, sh.tstart, sizeof(int32_t) * (sh.nsched + 1));
     MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
+    const int64_t groups = ceil_div64(nchains, (int64_t)WARPS * sh.lc);
+    MC3B_CHECK_ARG(groups <= 0x7fffffff, "too many chains for one launch");
+    A.f.on = 0;
+    if (o.fuse != nullptr) {
+        MC3B_CHECK_ARG(o.fuse_done != nullptr, "the fused Metropolis epilogue needs its counters (fuse_done)");
+        MC3B_CHECK_ARG(o.gen >= 0 || (o.fuse->gen_dev && o.fuse->thinning > 0),
+                       "device-driven generations need gen_dev and thinning");
+        MC3B_CHECK_ARG(!o.advance || o.fuse->gen_dev, "advance needs gen_dev");
+        MC3B_CHECK_ARG(o.c_off >= o.fuse->chain0 && o.c_off + nchains <= o.fuse->chain0 + o.fuse->nlocal,
+                       "chain range outside this device's slice");
+        A.f.on = 1; A.f.advance = o.advance; A.f.done = o.fuse_done; A.f.c_off = o.c_off;
+        A.f.gen = o.gen; A.f.zrow0 = o.zrow0; A.f.S = *o.fuse;
+    }
+    dim3 grid((unsigned)groups, (unsigned)nsplit), block(WARPS * 32);
     if (model_id == MC3B_MODEL_SINUSOID_GRID) {
         if constexpr (std::is_same<T, double>::value) {
-            if (sh.lc == 32 && a.use_tma && n >= 2) {
-                dim3 grid((unsigned)sh.groups, (unsigned)nsplit), block(WARPS * 32);
-                if (sh.cpt == 2) k_model_chisq<SineGridModel, double, 32, 2><<<grid, block, 0, st>>>(a);
-                else k_model_chisq<SineGridModel, double, 32, 1><<<grid, block, 0, st>>>(a);
-                MC3B_CHECK_LAUNCH("k_model_chisq<grid>");
-                return MC3B_OK;
+            if (sh.lc == 32 && A.use_tma && n >= 2) {
+                if (!getenv("MC3B_OLD_GRID"))
+                    return mc3b_launch_sinegrid(A, usig, (unsigned)groups, (unsigned)nsplit, st);
+                if (!usig) {                        // round-1 kernel, kept for A/B measurements
+                    k_model_chisq<SineGridModel, double, 32, 1, false><<<grid, block, 0, st>>>(A);
+                    MC3B_CHECK_LAUNCH("k_model_chisq<grid>");
+                    return MC3B_OK;
+                }
             }
         }
         model_id = MC3B_MODEL_SINUSOID;             // small populations, fp32, unaligned: plain model
     }
-    MC3B_DISPATCH_MODEL(T, model_id, nmodel, return (launch_model_chisq<M, T>(sh, a, nsplit, st)));
+    if (usig) { MC3B_DISPATCH_MODEL(T, model_id, nmodel, return (launch_model_chisq<M, T, true>(sh, A, grid, st))); }
+    else { MC3B_DISPATCH_MODEL(T, model_id, nmodel, return (launch_model_chisq<M, T, false>(sh, A, grid, st))); }
     return MC3B_OK;
 }
 
@@ -417,23 +418,33 @@ extern "C" int mc3b_model_chisq_splits(int64_t nchains, int64_t n, int dtype, in
     return MC3B_OK;
 }
 
-extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,
-                                int nmodel, const void* x, const void* data, const void* invsig, int64_t n,
-                                double* partial, int64_t ldpartial, int nsplit, void* stream) {
+extern "C" int mc3b_model_chisq_ex(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,
+                                   int nmodel, const void* x, const void* data, const void* invsig, int64_t n,
+                                   double* partial, int64_t ldpartial, int nsplit, const mc3b_chisq_opts_t* opts,
+                                   void* stream) {
     MC3B_CHECK_ARG(params && x && data && invsig && partial, "null pointer");
     MC3B_CHECK_ARG(ldpartial >= nchains, "ldpartial < nchains");
     MC3B_CHECK_ARG(nchains > 0 && n > 0 && nmodel > 0 && nmodel <= ldp, "bad sizes");
     MC3B_CHECK_ARG(mc3b_model_nparams(model_id, nmodel) == nmodel, "model %d does not take %d parameters",
                    model_id, nmodel);
+    mc3b_chisq_opts_t o = {};
+    if (opts) o = *opts;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MC3B_F64)
         return model_chisq_t<double>(model_id, params, ldp, nchains, nmodel, x, data, invsig, n, partial, ldpartial,
-                                     nsplit, dtype, st);
+                                     nsplit, dtype, o, st);
     if (dtype == MC3B_F32)
         return model_chisq_t<float>(model_id, params, ldp, nchains, nmodel, x, data, invsig, n, partial, ldpartial,
-                                    nsplit, dtype, st);
+                                    nsplit, dtype, o, st);
     mc3b_set_error("bad dtype %d", dtype);
     return MC3B_ERR_ARG;
+}
+
+extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,
+                                int nmodel, const void* x, const void* data, const void* invsig, int64_t n,
+                                double* partial, int64_t ldpartial, int nsplit, void* stream) {
+    return mc3b_model_chisq_ex(model_id, dtype, params, ldp, nchains, nmodel, x, data, invsig, n, partial,
+                               ldpartial, nsplit, nullptr, stream);
 }
 
 extern "C" int mc3b_model_eval(int model_id, const double* params, int64_t ldp, int64_t nchains, int nmodel,

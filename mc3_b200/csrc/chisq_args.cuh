@@ -1,0 +1,109 @@
+// mc3_b200 -- launch parameters and the fused Metropolis epilogue shared by the
+// model + chi-squared kernels (chisq.cu, chisq_grid.cu).
+#pragma once
+#include "models.cuh"
+#include "sampler_dev.cuh"
+
+namespace mc3b_chisq {
+
+#ifndef MC3B_WARPS
+#define MC3B_WARPS 4
+#endif
+#ifndef MC3B_RESIDENT
+#define MC3B_RESIDENT 6
+#endif
+#ifndef MC3B_RESIDENT2
+#define MC3B_RESIDENT2 4
+#endif
+#ifndef MC3B_LOOP_UNROLL
+#define MC3B_LOOP_UNROLL 2
+#endif
+#ifndef MC3B_TILE_F64
+#define MC3B_TILE_F64 128
+#endif
+constexpr int WARPS = MC3B_WARPS;
+constexpr int STAGES = 3;
+constexpr int LOOP_UNROLL = MC3B_LOOP_UNROLL;   // point groups of the inner loop unrolled together
+constexpr int RESIDENT = MC3B_RESIDENT;   // CTAs per SM the register budget is tuned for (ILP over occupancy)
+template <typename T> struct tilecfg { static constexpr int TILE = MC3B_TILE_F64; };   // fp64: 128 beat 256 by 6% (finer balance)
+template <> struct tilecfg<float> { static constexpr int TILE = 512; };
+
+constexpr int SCHED_MAX = 384;      // splits a size schedule can describe (else equal splits)
+// Optional epilogue of the model kernels: the LAST CTA of a chain group (the one
+// whose arrival completes the group's split count) adds the group's partial rows
+// in split order and takes the Metropolis step of its chains -- what k_metropolis
+// does, without the extra launch and without a second pass over `partial` from a
+// cold kernel; the last group to finish bumps the device generation counter
+// (replaces k_advance).  Same arithmetic, same order: identical bits.
+struct FuseArgs {
+    int on;
+    int advance;                    // bump *S.gen_dev when every group is done
+    int32_t* done;                  // [groups + 1] arrival counters; zero before the first launch, self-resetting
+    int64_t c_off;                  // global id of the chain in row 0 of params
+    int64_t gen, zrow0;             // as mc3b_metropolis (gen < 0: device-driven)
+    mc3b_sampler_t S;
+};
+
+template <typename T> struct ChisqArgs {
+    int nsched;                     // > 0: split y covers tiles [tstart[y], tstart[y+1])
+    int32_t tstart[SCHED_MAX + 1];
+    const double* params;
+    int64_t ldp, nchains;
+    const T *x, *d, *w;
+    int64_t n;
+    double* partial;
+    int64_t ldpartial;
+    int use_tma;
+    FuseArgs f;
+};
+
+// The Metropolis step itself, compiled once per translation unit: S points to the
+// CTA's shared-memory copy of the sampler description.
+static __device__ __noinline__ void fused_metropolis_tail(const mc3b_sampler_t* S, const double* partial, int64_t ldpartial,
+                                                   int nsplit, int64_t cl, int64_t c_off, int64_t gen,
+                                                   int64_t zrow0) {
+    if (gen < 0) {
+        gen = *S->gen_dev;
+        zrow0 = ((gen + 1) % S->thinning == 0) ? S->M0 + ((gen + 1) / S->thinning - 1) * S->nchains : -1;
+    }
+    const int64_t c = c_off + cl;
+    const double nxt = S->inb[c] ? sum_partials<true>(partial, ldpartial, nsplit, cl) : 0.0;
+    metropolis_chain(*S, nxt, gen, zrow0, c);
+}
+
+// chains_per_cta: chains a CTA covers (its thread t < chains_per_cta owns chain
+// blockIdx.x * chains_per_cta + t of the launch).  `f` must be the kernel
+// parameter itself (read from the constant bank, never copied to the stack).
+__device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double* partial, int64_t ldpartial,
+                                                 int64_t nchains, int chains_per_cta) {
+    __shared__ int s_last;
+    __shared__ __align__(16) mc3b_sampler_t sS;
+    __threadfence();                               // this CTA's partial row before its arrival
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&f.done[blockIdx.x], 1) == (int)gridDim.y - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) sS = f.S;                // constant bank -> shared, static offsets only
+    __syncthreads();
+    const int64_t cl = (int64_t)blockIdx.x * chains_per_cta + threadIdx.x;
+    if ((int)threadIdx.x < chains_per_cta && cl < nchains)
+        fused_metropolis_tail(&sS, partial, ldpartial, (int)gridDim.y, cl, f.c_off, f.gen, f.zrow0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        f.done[blockIdx.x] = 0;
+        if (f.advance) {
+            __threadfence();
+            if (atomicAdd(&f.done[gridDim.x], 1) == (int)gridDim.x - 1) {
+                f.done[gridDim.x] = 0;
+                *sS.gen_dev += 1;
+            }
+        }
+    }
+}
+
+}  // namespace mc3b_chisq
+using namespace mc3b_chisq;
+
+// chisq_grid.cu
+int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st);

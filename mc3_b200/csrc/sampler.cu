@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(128) k_metropolis(mc3b_sampler_t S, const doub
         gen = *S.gen_dev;
         zrow0 = ((gen + 1) % S.thinning == 0) ? S.M0 + ((gen + 1) / S.thinning - 1) * S.nchains : -1;
     }
-    metropolis_chain(S, partial, ldpartial, nsplit, c_off, gen, zrow0, c);
+    const double nxt = S.inb[c] ? sum_partials<false>(partial, ldpartial, nsplit, c - c_off) : 0.0;
+    metropolis_chain(S, nxt, gen, zrow0, c);
 }
 
 __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kickoff, int64_t ntrials, int64_t round,
@@ -65,6 +66,48 @@ __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kicko
 }
 
 __global__ void k_advance(int64_t* gen_dev) { *gen_dev += 1; }
+
+// Report-point counters of this device's chains in ONE small buffer (one D2H per
+// report instead of five): out = [sum naccept, best chisq, its generation, its
+// chain, best x (nfree), outbounds (nfree)].  Best = lowest chi-squared, ties to
+// the earlier (generation, chain) -- the order chain.py:268-274 would have met them.
+__global__ void __launch_bounds__(256) k_pack_counters(mc3b_sampler_t S, double* out) {
+    __shared__ double s_acc[256], s_chi[256];
+    __shared__ long long s_gen[256], s_ch[256];
+    const int t = threadIdx.x;
+    double acc = 0.0, chi = INFINITY;
+    long long gen = 0x7fffffffffffffffLL, ch = 0x7fffffffffffffffLL;
+    auto better = [](double c1, long long g1, long long h1, double c2, long long g2, long long h2) {
+        return c1 < c2 || (c1 == c2 && (g1 < g2 || (g1 == g2 && h1 < h2)));
+    };
+    for (int64_t c = S.chain0 + t; c < S.chain0 + S.nlocal; c += 256) {
+        acc += (double)S.naccept[c];
+        const double bc = S.best_chisq[c];
+        if (better(bc, S.best_gen[c], c, chi, gen, ch)) { chi = bc; gen = S.best_gen[c]; ch = c; }
+    }
+    s_acc[t] = acc; s_chi[t] = chi; s_gen[t] = gen; s_ch[t] = ch;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (t < o) {
+            s_acc[t] += s_acc[t + o];
+            if (better(s_chi[t + o], s_gen[t + o], s_ch[t + o], s_chi[t], s_gen[t], s_ch[t])) {
+                s_chi[t] = s_chi[t + o]; s_gen[t] = s_gen[t + o]; s_ch[t] = s_ch[t + o];
+            }
+        }
+        __syncthreads();
+    }
+    const bool any = s_chi[0] < INFINITY;
+    if (t == 0) {
+        out[0] = s_acc[0];
+        out[1] = s_chi[0];
+        out[2] = any ? (double)s_gen[0] : -1.0;
+        out[3] = any ? (double)s_ch[0] : -1.0;
+    }
+    if (t < S.nfree) {
+        out[4 + t] = any ? S.best_x[s_ch[0] * S.nfree + t] : 0.0;
+        out[4 + S.nfree + t] = (double)S.outbounds[t];
+    }
+}
 
 // log_prior of history rows (mc3/stats/stats.py:367-392) and the data chi-squared
 // it implies: lpr = -0.5 sum_j t_j^2 with t_j = (z-prior)/low|up for Gaussian
@@ -98,9 +141,10 @@ __global__ void __launch_bounds__(128) k_log_prior(const double* Z, int64_t nrow
 // sums over chains -> W, B, V, sqrt(V/W)   (gelman.py:75-92).
 __global__ void __launch_bounds__(128) k_gr_stats(const double* Z, int64_t nfree, int64_t nchains, int64_t M0,
                                                   const int64_t* rows, int64_t ldr, int64_t burnin, int64_t niter,
-                                                  double* work) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nchains * nfree) return;
+                                                  int64_t c_begin, int64_t c_end, double* work) {
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= (c_end - c_begin) * nfree) return;
+    const int64_t t = c_begin * nfree + t0;
     const int64_t c = t / nfree, p = t % nfree;
     auto at = [&](int64_t k) -> double {
         const int64_t row = rows ? rows[c * ldr + k] : M0 + k * nchains + c;
@@ -206,6 +250,14 @@ extern "C" int mc3b_advance(const mc3b_sampler_t* s, void* stream) {
     return MC3B_OK;
 }
 
+extern "C" int mc3b_pack_counters(const mc3b_sampler_t* s, double* out, void* stream) {
+    MC3B_CHECK_ARG(s && out, "bad arguments");
+    MC3B_CHECK_ARG(s->nfree > 0 && s->nfree <= MAXP, "nfree out of range");
+    k_pack_counters<<<1, 256, 0, (cudaStream_t)stream>>>(*s, out);
+    MC3B_CHECK_LAUNCH("k_pack_counters");
+    return MC3B_OK;
+}
+
 extern "C" int mc3b_log_prior(const double* Z, int64_t nrows, int nfree, const int32_t* ifree, const double* prior,
                               const double* priorlow, const double* priorup, const double* log_post, double* lpr,
                               double* chisq, void* stream) {
@@ -229,15 +281,30 @@ extern "C" int mc3b_init_trials(const mc3b_sampler_t* s, int kickoff, int64_t nt
     return MC3B_OK;
 }
 
+extern "C" int mc3b_gelman_rubin_moments(const double* Z, int64_t nfree, int64_t nchains, int64_t M0,
+                                         const int64_t* rows, int64_t ldr, int64_t burnin, int64_t niter,
+                                         int64_t c_begin, int64_t c_end, double* work, void* stream) {
+    MC3B_CHECK_ARG(Z && work && nfree > 0 && nchains > 1 && niter > 0 && burnin >= 0, "bad arguments");
+    MC3B_CHECK_ARG(c_begin >= 0 && c_begin <= c_end && c_end <= nchains, "bad chain range");
+    if (c_end == c_begin) return MC3B_OK;
+    k_gr_stats<<<(unsigned)ceil_div64((c_end - c_begin) * nfree, 128), 128, 0, (cudaStream_t)stream>>>(
+        Z, nfree, nchains, M0, rows, ldr, burnin, niter, c_begin, c_end, work);
+    MC3B_CHECK_LAUNCH("k_gr_stats");
+    return MC3B_OK;
+}
+
+extern "C" int mc3b_gelman_rubin_psrf(const double* work, int64_t nfree, int64_t nchains, int64_t niter,
+                                      double* psrf, void* stream) {
+    MC3B_CHECK_ARG(work && psrf && nfree > 0 && nchains > 1 && niter > 0, "bad arguments");
+    k_gr_psrf<<<(unsigned)nfree, 256, 0, (cudaStream_t)stream>>>(work, nfree, nchains, niter, psrf);
+    MC3B_CHECK_LAUNCH("k_gr_psrf");
+    return MC3B_OK;
+}
+
 extern "C" int mc3b_gelman_rubin(const double* Z, int64_t nfree, int64_t nchains, int64_t M0, const int64_t* rows,
                                  int64_t ldr, int64_t burnin, int64_t niter, double* work, double* psrf,
                                  void* stream) {
-    MC3B_CHECK_ARG(Z && work && psrf && nfree > 0 && nchains > 1 && niter > 0 && burnin >= 0, "bad arguments");
-    cudaStream_t st = (cudaStream_t)stream;
-    k_gr_stats<<<(unsigned)ceil_div64(nchains * nfree, 128), 128, 0, st>>>(Z, nfree, nchains, M0, rows, ldr, burnin,
-                                                                           niter, work);
-    MC3B_CHECK_LAUNCH("k_gr_stats");
-    k_gr_psrf<<<(unsigned)nfree, 256, 0, st>>>(work, nfree, nchains, niter, psrf);
-    MC3B_CHECK_LAUNCH("k_gr_psrf");
-    return MC3B_OK;
+    if (int rc = mc3b_gelman_rubin_moments(Z, nfree, nchains, M0, rows, ldr, burnin, niter, 0, nchains, work, stream))
+        return rc;
+    return mc3b_gelman_rubin_psrf(work, nfree, nchains, niter, psrf, stream);
 }

@@ -140,9 +140,29 @@ __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3
     S.inb[c] = inb;
 }
 
-// Metropolis step of chain c (chain.py:257-289).
-__device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, const double* partial, int64_t ldpartial,
-                                                 int nsplit, int64_t c_off, int64_t gen, int64_t zrow0, int64_t c) {
+// Data chi-squared of a proposal: the partial rows of the model kernel added in
+// split order (fixed order = identical bits wherever the sum is taken).  CG: read
+// through L2 (rows written by other SMs during the same kernel).
+template <bool CG>
+__device__ __forceinline__ double sum_partials(const double* partial, int64_t ldpartial, int nsplit, int64_t col) {
+    double nxt = 0.0;
+    const double* p = partial + col;
+    int s = 0;
+    for (; s + 8 <= nsplit; s += 8) {               // eight loads in flight, added in order
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = CG ? __ldcg(p + (int64_t)(s + k) * ldpartial) : p[(int64_t)(s + k) * ldpartial];
+#pragma unroll
+        for (int k = 0; k < 8; k++) nxt += v[k];
+    }
+    for (; s < nsplit; s++) nxt += CG ? __ldcg(p + (int64_t)s * ldpartial) : p[(int64_t)s * ldpartial];
+    return nxt;
+}
+
+// Metropolis step of chain c (chain.py:257-289); nxt_data = data chi-squared of its
+// proposal (unused when the proposal was out of bounds).
+__device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, double nxt_data, int64_t gen, int64_t zrow0,
+                                                 int64_t c) {
     const int nfree = S.nfree, npars = S.npars;
     const bool peer = S.X_peers != nullptr;
     const int64_t half = S.nchains * nfree;
@@ -151,8 +171,7 @@ __device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, const 
     bool accept = false;
     const double* np_ = S.nextp + c * npars;
     if (S.inb[c]) {
-        double nxt = 0.0;
-        for (int s = 0; s < nsplit; s++) nxt += partial[(int64_t)s * ldpartial + (c - c_off)];
+        double nxt = nxt_data;
         if (S.prior != nullptr) {                    // stats.py:208-216 + stats.h:90-109
             double pr = 0.0;
             for (int k = 0; k < npars; k++) {

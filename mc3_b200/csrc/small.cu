@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(SW * 32) k_run_small(mc3b_sampler_t G, const d
             }
         }
         __syncthreads();
-        if (tid < nch) metropolis_chain(S, chisq_new, nch, 1, 0, g, zrow0, tid);
+        if (tid < nch) metropolis_chain(S, chisq_new[tid], g, zrow0, tid);
         __syncthreads();
     }
     // state back to global memory

@@ -53,6 +53,20 @@ def to_host(t):
     return buf.numpy()
 
 
+def on_device(fn):
+    """Run a Population method with the population's device current: the C ABI
+    launches on the current CUDA device and on its current stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *args, **kwargs):
+        if torch.cuda.current_device() == self.dev.index:
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.dev):
+            return fn(self, *args, **kwargs)
+    return wrapped
+
+
 _DT = {'f64': _lib.F64, 'f32': _lib.F32, np.float64: _lib.F64, np.float32: _lib.F32}
 
 
@@ -62,12 +76,28 @@ class Population:
                  priorup=None, nchains=7, sampler='snooker', wlike=False,
                  fgamma=1.0, fepsilon=0.0, hsize=10, thinning=1, nzchain=1,
                  seed=0, dtype='f64', device=None, rank=0, world=1, group=None,
-                 reflect=False, M0=None, shard='chains'):
+                 reflect=False, M0=None, shard='chains', plan_chains=None):
         _lib.load()
         if not torch.cuda.is_available():
             raise _lib.Mc3bError('mc3_b200 needs a CUDA device (no CPU fallback)')
         self.dev = torch.device('cuda', torch.cuda.current_device()) \
             if device is None else torch.device(device)
+        if self.dev.type != 'cuda':
+            raise _lib.Mc3bError('mc3_b200 needs a CUDA device (no CPU fallback)')
+        if self.dev.index is None:
+            self.dev = torch.device('cuda', torch.cuda.current_device())
+        # every launch of this object goes to self.dev: the C ABI launches on the
+        # CURRENT device, so the public methods below switch to it (on_device)
+        with torch.cuda.device(self.dev):
+            self._init(data, uncert, func, params, indparams, indparams_dict, pstep,
+                       pmin, pmax, prior, priorlow, priorup, nchains, sampler, wlike,
+                       fgamma, fepsilon, hsize, thinning, nzchain, seed, dtype, rank,
+                       world, group, reflect, M0, shard, plan_chains)
+
+    def _init(self, data, uncert, func, params, indparams, indparams_dict, pstep,
+              pmin, pmax, prior, priorlow, priorup, nchains, sampler, wlike,
+              fgamma, fepsilon, hsize, thinning, nzchain, seed, dtype, rank,
+              world, group, reflect, M0, shard, plan_chains):
         self.rank, self.world, self.group = rank, world, group
         # shard='chains': each device owns a block of chains (population exchange
         # per generation).  shard='data': each device holds a slice of the data
@@ -82,6 +112,7 @@ class Population:
         self.indparams_dict = dict(indparams_dict or {})
         self.wlike = bool(wlike)
         self.sampler = sampler
+        self.usig = False
         self.dtype = _DT[dtype]
         f64 = dict(dtype=torch.float64, device=self.dev)
 
@@ -137,6 +168,10 @@ class Population:
             x = x[lo:hi]
             self.d_x = torch.from_numpy(x).to(self.dev)
             self.d_invsig = 1.0/self.d_uncert
+            # one uncertainty for all points: no weight stream, residuals are plain
+            # differences (mc3b_chisq_opts_t.uniform_sigma); MC3B_NO_USIG=1 disables
+            self.usig = bool(uncert.size > 0 and np.all(uncert == uncert[0])
+                             and not os.environ.get('MC3B_NO_USIG'))
             # A sinusoid on a uniform abscissa grid takes the rotation-recurrence
             # kernel (models.cuh SineGridModel); MC3B_NO_GRID=1 forces the plain one.
             self.chisq_model_id = func.model_id
@@ -219,6 +254,15 @@ class Population:
         self._plans = {}
         self._work = {}
         self._graph = None
+        # launch shape planned for `plan_chains` chains instead of the chains of each
+        # launch: identical chi-squared bits however the population is spread over
+        # launches / devices (include/mc3b200.h, mc3b_chisq_opts_t)
+        self.plan_chains = int(plan_chains) if plan_chains else 0
+        # Metropolis step fused into the tail of the model kernel (2 launches per
+        # generation instead of 4); MC3B_NO_FUSE=1 keeps the separate kernels
+        self.fused = (self.kind == 'builtin' and not self.wlike and self.shard == 'chains'
+                      and not os.environ.get('MC3B_NO_FUSE'))
+        self.fuse_done = torch.zeros(self.nlocal//8 + 8, dtype=torch.int32, device=self.dev)
         self.S = self._make_struct()
         self.set_jump_scales(fgamma, fepsilon)
         self.S.reflect = 1 if reflect else 0
@@ -296,8 +340,8 @@ class Population:
     def _plan(self, nb):
         if nb not in self._plans:
             ns = ctypes.c_int(0)
-            _lib.call('mc3b_model_chisq_plan', nb, self.ndata, self.dtype,
-                      ctypes.byref(ns))
+            _lib.call('mc3b_model_chisq_plan', max(self.plan_chains, nb), self.ndata,
+                      self.dtype, ctypes.byref(ns))
             self._plans[nb] = ns.value
         return self._plans[nb]
 
@@ -321,11 +365,14 @@ class Population:
                                 **self.indparams_dict)
         return torch.from_numpy(rows).to(self.dev)
 
-    def data_chisq(self, P):
-        """(partial, ld, nsplit) holding the data chi-squared of rows of P."""
+    @on_device
+    def data_chisq(self, P, fuse=None):
+        """(partial, ld, nsplit) holding the data chi-squared of rows of P.
+        fuse = (c_off, gen, zrow0, advance): the model kernel also takes the
+        Metropolis step of chains c_off .. c_off + len(P) (built-in models)."""
         if self.shard == 'data':
             return self._data_chisq_sharded(P)
-        return self._data_chisq_local(P)
+        return self._data_chisq_local(P, fuse)
 
     def _data_chisq_sharded(self, P):
         """Local-slice sums, then an all-gather of one fp64 per chain and device;
@@ -341,7 +388,7 @@ class Population:
         dist.all_gather_into_tensor(allsum.view(-1), allsum[self.rank], group=self.group)
         return allsum, nb, self.world
 
-    def _data_chisq_local(self, P):
+    def _data_chisq_local(self, P, fuse=None):
         nb = P.shape[0]
         st = _lib.stream_ptr()
         if self.wlike:
@@ -364,10 +411,19 @@ class Population:
         if self.kind == 'builtin':
             ns = self._plan(nb)
             part = self._workspace(('part', nb), (ns, nb))
-            _lib.call('mc3b_model_chisq', self.chisq_model_id, self.dtype,
+            o = _lib.ChisqOpts()
+            o.plan_chains = max(self.plan_chains, nb) if self.plan_chains else 0
+            o.uniform_sigma = 1 if self.usig else 0
+            if fuse is not None:
+                o.c_off, o.gen, o.zrow0, adv = fuse
+                o.advance = 1 if adv else 0
+                o.fuse = ctypes.pointer(self.S)
+                o.fuse_done = self.fuse_done.data_ptr()
+            _lib.call('mc3b_model_chisq_ex', self.chisq_model_id, self.dtype,
                       P.data_ptr(), _lib.ld(P), nb, self.nmodel,
                       self.k_x.data_ptr(), self.k_d.data_ptr(),
-                      self.k_w.data_ptr(), self.ndata, part.data_ptr(), nb, ns, st)
+                      self.k_w.data_ptr(), self.ndata, part.data_ptr(), nb, ns,
+                      ctypes.byref(o), st)
             self.launches += 1
             return part, nb, ns
         m = self._model_rows(P)
@@ -378,6 +434,7 @@ class Population:
         self.launches += 1
         return out, nb, 1
 
+    @on_device
     def chisq(self, P):
         """chi-squared + prior terms of full parameter vectors P [nb, npars]."""
         P = P.contiguous()
@@ -394,6 +451,7 @@ class Population:
     # ------------------------------------------------------------------
     # initial population   (mcmc_driver.py:229-278)
     # ------------------------------------------------------------------
+    @on_device
     def init_population(self, kickoff='normal'):
         kick = {'normal': 0, 'uniform': 1}[kickoff]
         M0 = self.M0
@@ -443,6 +501,7 @@ class Population:
         allgather_rows(buf, self.rank*per, per, self.group)
         return buf[:nt, 0].contiguous()
 
+    @on_device
     def set_initial(self, Z0, log_post0):
         """Install M0 initial history rows and start every chain from row c
         (chain.py:163-170: chain c starts at Z[c], chisq = -2 log_post[c])."""
@@ -480,14 +539,21 @@ class Population:
         c0, c1 = self.chain0, self.chain0 + self.nlocal
         zsize = self.M0 + (gen//self.thinning)*self.nchains if gen >= 0 else 0
         _lib.call('mc3b_propose', ctypes.byref(self.S), gen, zsize, c0, c1, st)
-        part, ld, ns = self.data_chisq(self.nextp[c0:c1])
+        self.launches += 1
         zrow0 = self._zrow0(gen) if gen >= 0 else -1
-        _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(), ld, ns,
-                  c0, gen, zrow0, c0, c1, st)
-        self.launches += 2
-        if self.world > 1 and self.shard == 'chains':
+        # the generation counter may advance inside the fused kernel only when no
+        # later launch of this generation reads it
+        exch = self.world > 1 and self.shard == 'chains'
+        if self.fused:
+            self.data_chisq(self.nextp[c0:c1], fuse=(c0, gen, zrow0, gen < 0 and not exch))
+        else:
+            part, ld, ns = self.data_chisq(self.nextp[c0:c1])
+            _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(), ld, ns,
+                      c0, gen, zrow0, c0, c1, st)
+            self.launches += 1
+        if exch:
             self._exchange(gen)
-        if gen < 0:
+        if gen < 0 and not (self.fused and not exch):
             _lib.call('mc3b_advance', ctypes.byref(self.S), st)
             self.launches += 1
 
@@ -530,6 +596,7 @@ class Population:
         self.launches = before
         return g, per
 
+    @on_device
     def run(self, ngen, use_graph=None):
         """Advance `ngen` generations.  Built-in models replay captured CUDA
         graphs; small problems (launch-latency bound) replay graphs that hold a
@@ -594,6 +661,7 @@ class Population:
     # ------------------------------------------------------------------
     # replay of the reference's recorded stream (sequential chain order)
     # ------------------------------------------------------------------
+    @on_device
     def replay(self, draws, ngen=None):
         """draws: dict of arrays from oracle DrawLog.arrays() (normal, a, b, iz,
         usj, gs, u, done).  Chains are stepped one at a time for demc/snooker
@@ -640,55 +708,90 @@ class Population:
     def zsize(self):
         return self.M0 + self.thinned_done()*self.nchains
 
-    def gather_history(self):
-        """Make Z / log_post / zchain complete on every device (no-op at world=1
-        and for data sharding, where the history is replicated)."""
-        if self.shard == 'data':
+    @on_device
+    def gather_history(self, dst=None):
+        """Make Z / log_post / zchain complete on every device, or on device `dst`
+        only (no-op at world=1 and for data sharding, where the history is
+        replicated).  Rows already complete (gathered earlier, or stored to every
+        device as they were written) are not sent again."""
+        if self.shard == 'data' or self.world == 1:
             return
+        K = self.thinned_done()
+        k0 = getattr(self, '_gathered_k', 0)      # thinned steps complete everywhere
+        if K <= k0:
+            return
+        lo = self.M0 + k0*self.nchains
         for t in (self.Z, self.log_post, self.zchain):
-            if t is self.Z and self.p2p is not None and 'z_hdl' in self.p2p:
-                continue                     # rows were stored to every device as they were written
-            gather_history(t, self.M0, self.thinned_done(), self.nchains,
-                           self.rank, self.world, self.group)
+            if t is self.Z and (self.sampler == 'snooker' or
+                                (self.p2p is not None and 'z_hdl' in self.p2p)):
+                continue                     # snooker exchanges its rows every generation
+            gather_history(t, lo, K - k0, self.nchains, self.rank, self.world,
+                           self.group, dst)
+        if dst is None:
+            self._gathered_k = K
+
+    def counters_async(self):
+        """Enqueue the report-point counters (one pack kernel, one collective at
+        world > 1, one D2H into pinned memory) and return a handle; nothing blocks.
+        counters_result(handle) turns it into the dictionary."""
+        with torch.cuda.device(self.dev):
+            n = 4 + 2*self.nfree
+            gathered = self.world > 1 and self.shard == 'chains'
+            rows = self.world if gathered else 1
+            buf = self._workspace('pack', (rows, n))
+            mine = buf[self.rank if gathered else 0]
+            _lib.call('mc3b_pack_counters', ctypes.byref(self.S), mine.data_ptr(),
+                      _lib.stream_ptr())
+            self.launches += 1
+            if gathered:
+                import torch.distributed as dist
+                if dist.get_backend(self.group) == 'nccl':
+                    dist.all_gather_into_tensor(buf.view(-1), mine, group=self.group)
+                else:
+                    parts = [torch.empty_like(mine) for _ in range(self.world)]
+                    dist.all_gather(parts, mine.clone(), group=self.group)
+                    buf.copy_(torch.stack(parts))
+            host = torch.empty((rows, n), dtype=torch.float64, pin_memory=True)
+            host.copy_(buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return host, ev
+
+    def counters_result(self, handle):
+        """chain.py:268-274 -- first strictly lower chi-squared in (generation,
+        chain) order wins, starting from the best of the initial population."""
+        host, ev = handle
+        ev.synchronize()
+        h = host.numpy()
+        nf = self.nfree
+        numaccept = int(round(h[:, 0].sum())) + getattr(self, 'resumed_accept', 0)
+        outbounds = np.rint(h[:, 4 + nf:4 + 2*nf].sum(axis=0)).astype(int)
+        best_chisq = -2.0*self.best_log_post0
+        bestp = np.copy(self.bestp0)
+        cand = [r for r in h if r[3] >= 0 and r[1] < best_chisq]
+        if cand:
+            r = min(cand, key=lambda r: (r[1], r[2], r[3]))
+            best_chisq = float(r[1])
+            bestp[self.ifree] = r[4:4 + nf]
+            for s in self.ishare:
+                bestp[s] = bestp[-int(self.pstep[s]) - 1]
+        return dict(numaccept=numaccept, outbounds=outbounds, bestp=bestp,
+                    best_log_post=-0.5*best_chisq)
 
     def counters(self):
         """Host copy of the counters (summed over devices)."""
-        nacc, oob = self.naccept, self.outbounds
-        bc, bx, bg = self.best_chisq, self.best_x, self.best_gen
-        if self.world > 1 and self.shard == 'chains':
-            import torch.distributed as dist
-            lo, n = self.chain0, self.nlocal
-            nacc, bg, bx = (sum_owned(t, lo, n, self.group) for t in (nacc, bg, bx))
-            fin = torch.where(torch.isfinite(bc), bc, torch.zeros_like(bc))
-            isf = sum_owned(torch.isfinite(bc).to(torch.float64), lo, n, self.group)
-            bc = sum_owned(fin, lo, n, self.group)
-            bc = torch.where(isf > 0, bc, torch.full_like(bc, float('inf')))
-            oob = oob.clone()
-            dist.all_reduce(oob, group=self.group)
-        bc_h = bc.cpu().numpy()
-        bg_h = bg.cpu().numpy()
-        numaccept = int(nacc.sum()) + getattr(self, 'resumed_accept', 0)
-        # chain.py:268-274 -- first strictly lower chi-squared in (generation,
-        # chain) order wins; start from the best of the initial population.
-        best_chisq = -2.0*self.best_log_post0
-        bestp = np.copy(self.bestp0)
-        cand = np.where(bc_h < best_chisq)[0]
-        if cand.size:
-            m = bc_h[cand].min()
-            tie = cand[bc_h[cand] == m]
-            c = tie[np.lexsort((tie, bg_h[tie]))[0]]
-            best_chisq = float(bc_h[c])
-            bestp[self.ifree] = bx[c].cpu().numpy()
-            for s in self.ishare:
-                bestp[s] = bestp[-int(self.pstep[s]) - 1]
-        return dict(numaccept=numaccept, outbounds=oob.cpu().numpy().astype(int),
-                    bestp=bestp, best_log_post=-0.5*best_chisq)
+        return self.counters_result(self.counters_async())
 
-    def history_host(self):
+    @on_device
+    def history_host(self, dst=None):
         """(posterior, zchain, log_post, chisq) of the valid rows as numpy arrays;
-        chisq = -2 (log_post - log_prior) comes from the device (mc3b_log_prior)."""
-        self.gather_history()
+        chisq = -2 (log_post - log_prior) comes from the device (mc3b_log_prior).
+        dst: only that device receives the other devices' rows and copies the
+        history to its host; the others return empty arrays."""
+        self.gather_history(dst)
         lo, hi = self.first_valid, self.zsize()
+        if dst is not None and self.world > 1 and self.rank != dst:
+            hi = lo
         if hi <= lo:
             z = np.zeros((0, self.nfree))
             return z, np.zeros(0, int), np.zeros(0), np.zeros(0)
@@ -702,6 +805,7 @@ class Population:
         return (to_host(self.Z[lo:hi]), to_host(self.zchain[lo:hi]).astype(int),
                 to_host(self.log_post[lo:hi]), to_host(chisq))
 
+    @on_device
     def sample_statistics(self, zburn, quantile=0.683):
         """median, mean, std and central-quantile bounds of the burned posterior,
         per free parameter, computed on the device over the lock-step block of
@@ -722,17 +826,68 @@ class Population:
                 blk.std(dim=0, unbiased=False).cpu().numpy(),
                 pct(0.5*(1 - quantile)), pct(0.5*(1 + quantile)))
 
+    def gelman_rubin_async(self, zburn):
+        """PSRF per free parameter over every chain's samples after burn-in
+        (gelman.py:36-92), left on the device: returns (pinned host tensor, event)
+        or None when there are not enough samples.  Each device reduces ITS chains
+        to mean / variance; with the chains partitioned over devices the two
+        [nchains, nfree] moment blocks are all-gathered (not the history) and every
+        device evaluates the same fixed-order sums over all chains."""
+        with torch.cuda.device(self.dev):
+            K = self.thinned_done()
+            rows, ldr, burn = None, 0, zburn
+            if self.first_valid == 0:        # resumed run: earlier samples count (chain.py:166-169)
+                rows_t, counts = self._resumed_rows()
+                niter = int(counts.min()) - zburn
+                rows, ldr = rows_t.data_ptr(), rows_t.shape[1]
+            else:
+                niter = K - zburn
+            if niter < 1:
+                return None
+            st = _lib.stream_ptr()
+            work = self._workspace('gr', (2, self.nchains, self.nfree))
+            c0, c1 = self.chain0, self.chain0 + self.nlocal
+            _lib.call('mc3b_gelman_rubin_moments', self.Z.data_ptr(), self.nfree, self.nchains,
+                      self.M0, rows, ldr, burn, niter, c0, c1, work.data_ptr(), st)
+            if self.world > 1 and self.shard == 'chains':
+                allgather_rows(work[0], self.chain0, self.nlocal, self.group)
+                allgather_rows(work[1], self.chain0, self.nlocal, self.group)
+            psrf = self._workspace('psrf', (self.nfree,))
+            _lib.call('mc3b_gelman_rubin_psrf', work.data_ptr(), self.nfree, self.nchains,
+                      niter, psrf.data_ptr(), st)
+            self.launches += 2
+            host = torch.empty(self.nfree, dtype=torch.float64, pin_memory=True)
+            host.copy_(psrf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return host, ev
+
+    def _resumed_rows(self):
+        """Row table [nchains, count] of a resumed history: each chain's earlier
+        samples in file order, then its new rows (lock-step layout)."""
+        K = self.thinned_done()
+        old = self.resumed_rows            # list of int64 arrays, one per chain
+        counts = np.array([len(o) for o in old]) + K
+        n = int(counts.min())
+        tab = np.empty((self.nchains, n), dtype=np.int64)
+        new = self.M0 + np.arange(K)[None, :]*self.nchains + np.arange(self.nchains)[:, None]
+        for c in range(self.nchains):
+            tab[c] = np.concatenate([old[c], new[c]])[:n]
+        return torch.from_numpy(tab).to(self.dev), counts
+
+    def chain_counts_min(self):
+        """Samples per chain as the reference's `chainsize` counts them, minus hsize
+        (mcmc_driver.py:178-184, 325): thinned generations done, plus on a resumed
+        run the shortest chain of the file."""
+        K = self.thinned_done()
+        if self.first_valid == 0:
+            return K + min(len(o) for o in self.resumed_rows) - self.hsize
+        return K
+
     def gelman_rubin(self, zburn):
         """PSRF per free parameter over the thinned samples after burn-in."""
-        K = self.thinned_done()
-        niter = K - zburn
-        if niter < 1:
+        h = self.gelman_rubin_async(zburn)
+        if h is None:
             return np.zeros(self.nfree)
-        self.gather_history()
-        work = self._workspace('gr', (2, self.nchains, self.nfree))
-        psrf = torch.empty(self.nfree, dtype=torch.float64, device=self.dev)
-        _lib.call('mc3b_gelman_rubin', self.Z.data_ptr(), self.nfree, self.nchains,
-                  self.M0, None, 0, zburn, niter, work.data_ptr(), psrf.data_ptr(),
-                  _lib.stream_ptr())
-        self.launches += 2
-        return psrf.cpu().numpy()
+        h[1].synchronize()
+        return h[0].numpy().copy()

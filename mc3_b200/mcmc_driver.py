@@ -157,32 +157,60 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
         print("Yippee Ki Yay Monte Carlo!")
     log.msg(f"Start MCMC chains  ({time.ctime()})")
     # Reports every tenth of the run, on whole thinned generations (:297-348).
+    # A report is enqueued behind its block of generations (one pack kernel, the
+    # Gelman-Rubin kernels, one D2H each into pinned memory) and printed when its
+    # copies have landed: the device never waits for the host between blocks.  The
+    # host only blocks where the reference's control flow needs the numbers: a
+    # savefile to write, or a grbreak decision.
     step_k = max(1, int(np.ceil(nzchain/10)))
     k_done = 0
+    pending = []
+
+    def flush(block):
+        """Print finished reports in order; True when one of them stops the run."""
+        while pending:
+            kd, hc, hg, zs = pending[0]
+            if not block and not (hc[1].query() and (hg is None or hg[1].query())):
+                return False
+            pending.pop(0)
+            c = pop.counters_result(hc)
+            log.progressbar(kd/nzchain)
+            log.msg(
+                f"Out-of-bound Trials:\n{c['outbounds']}\n"
+                f"Best Parameters: (chisq={-2*c['best_log_post']:.4f})\n"
+                f"{c['bestp'][ifree]}", width=80)
+            if hg is not None:
+                hg[1].synchronize()
+                psrf = hg[0].numpy()
+                log.msg(f"Gelman-Rubin statistics for free parameters:\n{psrf}",
+                        width=80)
+                if np.all(psrf < 1.01):
+                    log.msg("All parameters converged to within 1% of unity.")
+                if grbreak > 0.0 and np.all(psrf < grbreak) and zs > grnmin:
+                    log.msg(
+                        "\nAll parameters satisfy the GR convergence "
+                        f"threshold of {grbreak:g}, stopping the MCMC.")
+                    pending.clear()
+                    return True
+        return False
+
     while k_done < nzchain:
         k_next = min(nzchain, k_done + step_k)
         pop.run((k_next - k_done)*thinning, use_graph=use_graph)
         k_done = k_next
-        c = pop.counters()
-        log.progressbar(k_done/nzchain)
-        log.msg(
-            f"Out-of-bound Trials:\n{c['outbounds']}\n"
-            f"Best Parameters: (chisq={-2*c['best_log_post']:.4f})\n"
-            f"{c['bestp'][ifree]}", width=80)
-        if savefile is not None and rank == 0:
-            update_output(output, pop, hsize, c)
-            np.savez(savefile, **output)
-        if grtest and k_done > zburn:
-            psrf = pop.gelman_rubin(zburn)
-            log.msg(f"Gelman-Rubin statistics for free parameters:\n{psrf}",
-                    width=80)
-            if np.all(psrf < 1.01):
-                log.msg("All parameters converged to within 1% of unity.")
-            if grbreak > 0.0 and np.all(psrf < grbreak) and pop.zsize() > grnmin:
-                log.msg(
-                    "\nAll parameters satisfy the GR convergence "
-                    f"threshold of {grbreak:g}, stopping the MCMC.")
-                break
+        hc = pop.counters_async()
+        hg = None
+        if grtest and pop.chain_counts_min() > zburn:          # :325
+            hg = pop.gelman_rubin_async(zburn)
+        pending.append((k_done, hc, hg, pop.zsize()))
+        if savefile is not None:
+            # every device takes part (the history gather is collective); rank 0 writes
+            flush(True)
+            update_output(output, pop, hsize, pop.counters())
+            if rank == 0:
+                np.savez(savefile, **output)
+        if flush(block=(grbreak > 0.0 and hg is not None) or k_done == nzchain):
+            break
 
     nburned = update_output(output, pop, hsize)
     Z = output['posterior']
@@ -213,7 +241,12 @@ def _resume(pop, oldrun):
     pop.Z[:M0] = torch.as_tensor(zold, device=pop.dev)
     pop.log_post[:M0] = torch.as_tensor(lp, device=pop.dev)
     pop.zchain[:M0] = torch.as_tensor(zc, dtype=torch.int32, device=pop.dev)
-    last = np.array([np.where(zc == c)[0][-1] for c in range(pop.nchains)])
+    order = np.argsort(zc, kind='stable')           # each chain's rows, in file order
+    zs = zc[order]
+    lo = np.searchsorted(zs, np.arange(pop.nchains), side='left')
+    hi = np.searchsorted(zs, np.arange(pop.nchains), side='right')
+    pop.resumed_rows = [order[a:b].astype(np.int64) for a, b in zip(lo, hi)]
+    last = np.array([r[-1] for r in pop.resumed_rows])
     pop.X.copy_(pop.Z[torch.as_tensor(last, device=pop.dev)])
     pop.chisq_cur.copy_(-2.0*pop.log_post[torch.as_tensor(last, device=pop.dev)])
     pop.bestp0 = np.array(oldrun['bestp'], float)

@@ -35,8 +35,9 @@ def allgather_rows(block, chain0, nlocal, group=None):
         block.copy_(torch.cat(parts).view_as(block))
 
 
-def gather_history(t, M0, K, nchains, rank, world, group=None):
-    """Complete the thinned history tensor t ([zlen] or [zlen, w]) on every rank.
+def gather_history(t, M0, K, nchains, rank, world, group=None, dst=None):
+    """Complete the thinned history tensor t ([zlen] or [zlen, w]) on every rank
+    (dst=None) or on rank `dst` only (the other ranks just send their rows).
     Row M0 + k*nchains + c belongs to the owner of chain c; K thinned steps."""
     if world == 1 or K == 0:
         return
@@ -44,9 +45,16 @@ def gather_history(t, M0, K, nchains, rank, world, group=None):
     w = 1 if t.dim() == 1 else t.shape[1]
     v = t[M0:M0 + K*nchains].view(K, world, nlocal*w)
     mine = v[:, rank].contiguous()
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine, group=group)
-    v.copy_(torch.stack(parts, dim=1))
+    if dst is None:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        v.copy_(torch.stack(parts, dim=1))
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+        dist.gather(mine, parts, dst=dist.get_global_rank(group, dst) if group is not None else dst,
+                    group=group)
+        if rank == dst:
+            v.copy_(torch.stack(parts, dim=1))
 
 
 def sum_owned(t, chain0, nlocal, group=None):

@@ -109,6 +109,35 @@ def test_sampler_struct_layout_matches_header():
     assert names == [f[0] for f in _lib.SamplerStruct._fields_]
 
 
+def test_chisq_opts_layout_matches_header():
+    text = open(os.path.join(ROOT, 'include', 'mc3b200.h')).read()
+    body = text[text.index('typedef struct mc3b_chisq_opts {'):text.index('} mc3b_chisq_opts_t;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    names = []
+    for decl in body.split('{', 1)[1].split(';'):
+        decl = decl.strip()
+        if decl:
+            for part in decl.split(','):
+                names.append(re.findall(r'[A-Za-z_0-9]+', part)[-1])
+    assert names == [f[0] for f in _lib.ChisqOpts._fields_]
+    import ctypes
+    assert ctypes.sizeof(_lib.ChisqOpts) == 56
+
+
+def test_plan_is_a_function_of_plan_chains_only():
+    """The split boundaries of a launch planned for the whole population do not
+    depend on how many chains the launch holds (include/mc3b200.h, plan_chains)."""
+    import ctypes
+    import numpy as np
+    out = []
+    for _ in range(2):
+        buf = (ctypes.c_int64*512)()
+        ns = ctypes.c_int(0)
+        _lib.call('mc3b_model_chisq_splits', 4096, 100000, _lib.F64, buf, 512, ctypes.byref(ns))
+        out.append(np.array(buf[:ns.value + 1]))
+    assert np.array_equal(out[0], out[1])
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-box behaviour')
 def test_no_cpu_fallback():
     import numpy as np
