@@ -244,14 +244,18 @@ def run_ours(args):
                      w['priorup'], nchains=nchains, sampler=w['sampler'],
                      fepsilon=w['fepsilon'], thinning=1, nzchain=W + K + 1, seed=1234,
                      dtype=args.dtype, rank=rank, world=world)
+    # clock sampler: started before the warm-up and stopped after the kernel-alone
+    # timing, so that even a 4 ms timed region is bracketed by samples taken under
+    # load of the same kernels (at least 3 samples are required below)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    parity = multi_gpu_parity(args, w, model, rank, world, dev) if world > 1 else None
     pop.init_population('normal')
     pop.run(W, use_graph=True)                   # warm-up (captures the generation graph)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = pop.launches
     barrier()
     for k in range(K):
@@ -260,7 +264,6 @@ def run_ours(args):
         pop.run(1, use_graph=True)
         ev[k][1].record()
     barrier()
-    ck = clocks.stop() if rank == 0 else None
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -326,6 +329,15 @@ def run_ours(args):
                 'hbm_stream_GBs': 24.0*n/(kms*1e-3)/1e9,
                 'hbm_peak_GBs': _measured_peaks().get('hbm_gbs')}
 
+    ck = None
+    if rank == 0:
+        t_end = time.perf_counter() + 0.5
+        while len(clocks.rows) < 3 and time.perf_counter() < t_end:
+            pop.data_chisq(pop.nextp[pop.chain0:pop.chain0 + pop.nlocal])   # same kernel, untimed
+            torch.cuda.synchronize(dev)
+        ck = clocks.stop()
+        ck['window'] = 'warm-up + timed generations + kernel-alone timing (10 ms NVML polls)'
+
     # ---- end to end through the public hub call, host buffers ------------
     barrier()
     host = {k: np.array(w[k]) for k in ('data', 'uncert', 'x', 'params', 'pstep', 'pmin',
@@ -385,22 +397,75 @@ def run_ours(args):
                        'nchains_per_gpu': NCHAINS_PER_GPU, 'ndata': n,
                        'sampler': w['sampler'], 'model': w['model'],
                        'l2': 'flushed between timed steps (256 MB write, untimed)',
-                       'parallelism': f'chains partitioned over {world} GPU(s); '
-                                      'NCCL all-gather of the population per generation'
+                       'parallelism': (f'chains partitioned over {world} GPU(s); '
+                                       + ('next states stored into every device over NVLink by the '
+                                          'Metropolis epilogue, generation flags instead of a collective'
+                                          if pop.p2p is not None else
+                                          'NCCL all-gather of the population per generation'))
                                       if world > 1 else 'single GPU'},
             'chisq_evals_per_s': value*n,
             'acceptance_rate_pct': 100.0*acc/(nchains*(W + K)),
             'e2e': e2e, 'gpu_launches': launches, 'clocks': ck,
             'roofline': roof, 'cpu_baseline': cpu,
         }
+        if parity is not None:
+            line['multi_gpu_parity'] = parity
         _emit(line)
     if world > 1:
-        # Tearing NCCL down while captured graphs still reference the communicator
-        # can block; everything is reported, so leave without running destructors.
+        # captured graphs first (they may hold NCCL kernels), then the process group
         dist.barrier()
+        pop.close()
+        del pop
         torch.cuda.synchronize(dev)
-        sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
+
+
+def multi_gpu_parity(args, w, model, rank, world, dev):
+    """Driver-visible check that N devices compute what one device computes: a short
+    fixed-seed config-2 population (4096 chains in total, N=1e5: TMA path, decreasing
+    split schedule) run on all ranks and on rank 0 alone, launch shape planned for the
+    whole population; history compared byte for byte, and sampled rows' chi-squared
+    against the oracle (used here as the checker only)."""
+    import torch
+    import torch.distributed as dist
+    import mc3_b200 as mc3
+    from mc3_b200.mcmc_driver import mcmc
+    nch, ngen = 4096, 6
+    quiet = mc3.Log(verb=-1)
+
+    def run(rk, wd):
+        with contextlib.redirect_stdout(sys.stderr):
+            return mcmc(w['data'], w['uncert'], model, w['params'], [w['x']], {},
+                        w['pmin'], w['pmax'], w['pstep'], w['prior'], w['priorlow'],
+                        w['priorup'], nch, None, nch*ngen, w['sampler'], False, None, True, 0.0,
+                        0.5, 0, 1, 1.0, w['fepsilon'], 2, 'normal', None, False, quiet, None, None,
+                        seed=4242, dtype=args.dtype, rank=rk, world=wd, plan_chains=nch)
+    multi = run(rank, world)
+    dist.barrier()
+    res = None
+    if rank == 0:
+        single = run(0, 1)
+        eq = {k: bool(np.array_equal(multi[k], single[k])) for k in ('posterior', 'zchain', 'log_post')}
+        from oracle import kernels as ok
+        from oracle import models as om
+        rs = np.random.RandomState(1)
+        rows = rs.choice(multi['posterior'].shape[0], 4, replace=False)
+        worst = 0.0
+        for r in rows:
+            p = np.array(w['params'], float)
+            p[:] = multi['posterior'][r]                 # all five parameters are free
+            want = ok.chisq(om.sinusoid(p, w['x']), w['data'], w['uncert'], p, w['prior'],
+                            w['priorlow'], w['priorup'])
+            got = -2.0*multi['log_post'][r]
+            worst = max(worst, abs(got - want)/abs(want))
+        res = {'bitwise_equal_to_1gpu': all(eq.values()), 'equal': eq,
+               'oracle_rel_err': worst, 'nchains': nch, 'generations': ngen, 'ndata': int(w['x'].size),
+               'rows_checked_against_oracle': [int(r) for r in rows],
+               'exchange': 'peer-memory stores + generation flags' if os.environ.get('MC3B_P2P', '1') != '0'
+                           else 'NCCL all-gather'}
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    return res
 
 
 _OUT = None
@@ -415,7 +480,7 @@ def _emit(line):
 def _profile_summary():
     """dram bytes per launch of the dominant kernel from the committed ncu capture."""
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'r1_model_chisq.json')))
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r2_model_chisq.json')))
     except Exception:
         return {}
 

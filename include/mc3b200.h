@@ -194,6 +194,14 @@ typedef struct mc3b_sampler {
     double* const* X_peers;
     double* const* Z_peers;
     int32_t world, rank;
+    /* Generation flags of the peer-memory exchange: NULL, or [world] device pointers
+     * to every device's int64[world] flag array.  flag[p] on a device = generations
+     * device p has completed with all its peer stores performed.  The kernel that
+     * ends a generation (mc3b_model_chisq_ex with fuse + advance, or mc3b_advance)
+     * writes gen+1 into flag[rank] of EVERY device (release, system scope);
+     * mc3b_propose of generation gen waits until its own device's flags all read
+     * >= gen (acquire): no barrier kernel, no collective call per generation. */
+    int64_t* const* F_peers;
 } mc3b_sampler_t;
 
 /* Recorded random stream of one generation (replay mode), indexed by global
@@ -238,6 +246,17 @@ int mc3b_propose_replay(const mc3b_sampler_t* s, const mc3b_draws_t* d,
 int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial,
                     int64_t ldpartial, int nsplit, int64_t c_off, int64_t gen,
                     int64_t zrow0, int64_t c_begin, int64_t c_end, void* stream);
+
+/* Peer memory for the exchange above, mapped with CUDA IPC (one process per GPU of
+ * one box).  mc3b_peer_alloc: zero-filled device buffer on the current device +
+ * its 64-byte IPC handle [host].  mc3b_peer_open: map another process's buffer
+ * into this one (peer access is enabled on demand); *ptr [host] receives the local
+ * address.  mc3b_peer_close / mc3b_peer_free undo them.  These four are the only
+ * entry points that allocate. */
+int mc3b_peer_alloc(int64_t nbytes, void** ptr, unsigned char* handle64);
+int mc3b_peer_open(const unsigned char* handle64, void** ptr);
+int mc3b_peer_close(void* ptr);
+int mc3b_peer_free(void* ptr);
 
 /* Report-point counters of this device's chains, packed for one D2H copy
  * (replaces the hub's reads of the shared numaccept / outbounds / bestp arrays,
@@ -346,6 +365,24 @@ int mc3b_binrms(const double* data, int64_t n, int64_t maxbins,
 int mc3b_binarray(const double* data, int64_t n, int64_t binsize,
                   const double* uncert, double* bindata, double* binstd,
                   void* stream);
+
+/* ------------------------------------------------------------------------
+ * Posterior statistics   (replace the scipy/numpy path of stats.py:433-467, 764-802)
+ * ---------------------------------------------------------------------- */
+
+/* Bytes of workspace for mc3b_hpd. */
+int64_t mc3b_hpd_workspace(int nfree);
+
+/* Highest-posterior-density statistics of the marginals of posterior [n, nfree]
+ * (row-major fp64), per column as the reference's cred_region + marginal_statistics
+ * ('max_like'): Gaussian kernel density with Scott's bandwidth (scipy.stats.
+ * gaussian_kde) on every (n/120000)-th sample, traced at 100 points inside
+ * [max(mean - 6 std, min), min(mean + 6 std, max)], resampled linearly to 3000
+ * points, density threshold where the descending running sum reaches `quantile`
+ * of the total.  out [3, nfree]: mode, lowest and highest point above the
+ * threshold. */
+int mc3b_hpd(const double* posterior, int64_t n, int nfree, double quantile,
+             void* workspace, double* out, void* stream);
 
 /* ------------------------------------------------------------------------
  * Roofline denominators

@@ -38,6 +38,7 @@ class SamplerStruct(ctypes.Structure):
         ('best_x', c_vp), ('best_gen', c_vp),
         ('gen_dev', c_vp), ('thinning', c_i64),
         ('X_peers', c_vp), ('Z_peers', c_vp), ('world', c_i32), ('rank', c_i32),
+        ('F_peers', c_vp),
     ]
 
 
@@ -80,6 +81,10 @@ _SIGS = {
                                     ctypes.POINTER(DrawsStruct), c_i64, c_i64, c_vp]),
     'mc3b_metropolis': (c_int, [ctypes.POINTER(SamplerStruct), c_vp, c_i64, c_int,
                                 c_i64, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    'mc3b_peer_alloc': (c_int, [c_i64, ctypes.POINTER(c_vp), ctypes.c_char_p]),
+    'mc3b_peer_open': (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    'mc3b_peer_close': (c_int, [c_vp]),
+    'mc3b_peer_free': (c_int, [c_vp]),
     'mc3b_pack_counters': (c_int, [ctypes.POINTER(SamplerStruct), c_vp, c_vp]),
     'mc3b_advance': (c_int, [ctypes.POINTER(SamplerStruct), c_vp]),
     'mc3b_run_small': (c_int, [ctypes.POINTER(SamplerStruct), c_int, c_int, c_vp, c_vp, c_vp,
@@ -101,6 +106,8 @@ _SIGS = {
     'mc3b_binrms': (c_int, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                             c_vp, c_vp, c_vp]),
     'mc3b_binarray': (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    'mc3b_hpd_workspace': (c_i64, [c_int]),
+    'mc3b_hpd': (c_int, [c_vp, c_i64, c_int, c_dbl, c_vp, c_vp, c_vp]),
     'mc3b_fma_peak': (c_int, [c_int, c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
     'mc3b_fma_peak_variant': (c_int, [c_int, c_i64, c_vp, ctypes.POINTER(c_dbl), c_vp]),
 }

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libmc3b200.so')
-SOURCES = ['runtime.cu', 'chisq.cu', 'chisq_grid.cu', 'sampler.cu', 'small.cu', 'dwt.cu', 'timeavg.cu']
+SOURCES = ['runtime.cu', 'chisq.cu', 'chisq_grid.cu', 'sampler.cu', 'small.cu', 'dwt.cu', 'timeavg.cu', 'poststat.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo',
     '-std=c++17', '-Xcompiler', '-fPIC', '--fmad=true',

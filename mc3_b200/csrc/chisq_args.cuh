@@ -96,7 +96,10 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
             __threadfence();
             if (atomicAdd(&f.done[gridDim.x], 1) == (int)gridDim.x - 1) {
                 f.done[gridDim.x] = 0;
-                *sS.gen_dev += 1;
+                __threadfence();
+                const int64_t g = *sS.gen_dev + 1;
+                *sS.gen_dev = g;
+                if (sS.F_peers) flags_publish(sS, g);    // every group's peer stores are performed
             }
         }
     }

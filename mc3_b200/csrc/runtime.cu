@@ -31,6 +31,40 @@ extern "C" int mc3b_version(void) { return MC3B_VERSION; }
 extern "C" const char* mc3b_last_error(void) { return g_err; }
 extern "C" int mc3b_device_sms(void) { return mc3b_sm_count(); }
 
+// ---- peer memory (CUDA IPC) for the multi-GPU exchange ------------------------
+extern "C" int mc3b_peer_alloc(int64_t nbytes, void** ptr, unsigned char* handle64) {
+    MC3B_CHECK_ARG(nbytes > 0 && ptr && handle64, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    MC3B_CUDA(cudaMalloc(&p, (size_t)nbytes));
+    MC3B_CUDA(cudaMemset(p, 0, (size_t)nbytes));
+    MC3B_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    MC3B_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return MC3B_OK;
+}
+extern "C" int mc3b_peer_open(const unsigned char* handle64, void** ptr) {
+    MC3B_CHECK_ARG(handle64 && ptr, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    MC3B_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *ptr = p;
+    return MC3B_OK;
+}
+extern "C" int mc3b_peer_close(void* ptr) {
+    MC3B_CHECK_ARG(ptr, "null pointer");
+    MC3B_CUDA(cudaIpcCloseMemHandle(ptr));
+    return MC3B_OK;
+}
+extern "C" int mc3b_peer_free(void* ptr) {
+    MC3B_CHECK_ARG(ptr, "null pointer");
+    MC3B_CUDA(cudaFree(ptr));
+    return MC3B_OK;
+}
+
 // Roofline denominator: 8 independent accumulators per thread, each a chain of
 // dependent FMAs; 256 threads x 8 CTAs per SM keeps the pipe full.
 namespace {

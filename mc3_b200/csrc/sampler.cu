@@ -18,11 +18,12 @@ template <bool REPLAY>
 __global__ void __launch_bounds__(128) k_propose(mc3b_sampler_t S, mc3b_draws_t D, int64_t gen, int64_t zsize,
                                                  int64_t c_begin, int64_t c_end) {
     const int64_t c = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c_end) return;
     if (gen < 0) {                                   // device-driven generation (graph mode)
         gen = *S.gen_dev;
         zsize = S.M0 + (gen / S.thinning) * S.nchains;
     }
+    if (!REPLAY && S.F_peers) flags_wait(S, gen);    // every device has finished generation gen-1
+    if (c >= c_end) return;
     propose_chain<REPLAY>(S, D, gen, zsize, c);
 }
 
@@ -65,7 +66,11 @@ __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kicko
     ok[t] = good;
 }
 
-__global__ void k_advance(int64_t* gen_dev) { *gen_dev += 1; }
+__global__ void k_advance(mc3b_sampler_t S) {
+    const int64_t g = *S.gen_dev + 1;
+    *S.gen_dev = g;
+    if (S.F_peers) flags_publish(S, g);              // k_metropolis (previous launch) has stored everywhere
+}
 
 // Report-point counters of this device's chains in ONE small buffer (one D2H per
 // report instead of five): out = [sum naccept, best chisq, its generation, its
@@ -245,7 +250,7 @@ extern "C" int mc3b_metropolis(const mc3b_sampler_t* s, const double* partial, i
 
 extern "C" int mc3b_advance(const mc3b_sampler_t* s, void* stream) {
     MC3B_CHECK_ARG(s && s->gen_dev, "no device generation counter");
-    k_advance<<<1, 1, 0, (cudaStream_t)stream>>>(s->gen_dev);
+    k_advance<<<1, 1, 0, (cudaStream_t)stream>>>(*s);
     MC3B_CHECK_LAUNCH("k_advance");
     return MC3B_OK;
 }

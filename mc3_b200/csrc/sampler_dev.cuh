@@ -20,6 +20,25 @@ __device__ __forceinline__ void box_muller(double u1, double u2, double& n0, dou
     n1 = r * s;
 }
 
+// Peer-memory exchange: generation flags (include/mc3b200.h, F_peers).
+__device__ __forceinline__ void flags_publish(const mc3b_sampler_t& S, int64_t done) {
+    __threadfence_system();                          // this device's peer stores first
+    for (int p = 0; p < S.world; p++)
+        asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(S.F_peers[p] + S.rank), "l"((long long)done)
+                     : "memory");
+}
+// every thread of the CTA calls it (one thread per peer polls, then a CTA barrier)
+__device__ __forceinline__ void flags_wait(const mc3b_sampler_t& S, int64_t gen) {
+    if ((int)threadIdx.x < S.world) {
+        const int64_t* f = S.F_peers[S.rank] + threadIdx.x;
+        long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+        } while (v < (long long)gen);
+    }
+    __syncthreads();
+}
+
 // Proposal of chain c for generation gen (chain.py:185-247, 251-255).
 template <bool REPLAY>
 __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,

@@ -210,25 +210,26 @@ class Population:
 
         # ---- population state ----
         n = self.nchains
-        # Multi-GPU chain partition, opt-in peer-memory exchange (MC3B_P2P=1):
-        # population (and, for snooker, history) live in symmetric memory so that
-        # k_metropolis stores every chain's next state straight into all peers over
-        # NVLink; a signal-pad barrier per generation replaces the NCCL all-gather.
-        # Measured at 2 GPUs: 0.3108 vs 0.3151 ms per generation (config 2).  Off by
-        # default in round 1: one of four 2-GPU test launches stalled in it.
+        # Multi-GPU chain partition: population (and, for snooker, history) live in
+        # peer memory mapped into every process (CUDA IPC), so that the Metropolis step
+        # stores every chain's next state straight into all devices over NVLink and a
+        # generation flag per device orders the exchange: the next proposal kernel
+        # waits on the flags -- no barrier kernel and no NCCL call per generation.
+        # MC3B_P2P=0 falls back to the NCCL all-gather.
         self.p2p = None
         self._Xsym = None
-        if world > 1 and self.shard == 'chains' and os.environ.get('MC3B_P2P') == '1':
+        if world > 1 and self.shard == 'chains' and sampler != 'mrw' \
+                and os.environ.get('MC3B_P2P', '1') != '0':
             try:
                 self.p2p = self._setup_p2p(n, nfree)
-            except Exception as e:                      # no P2P / symmetric memory: NCCL path
+            except Exception as e:                      # no peer access: NCCL path
                 if rank == 0:
                     print(f'mc3_b200: peer-memory exchange unavailable ({e}); using NCCL all-gather')
                 self.p2p = None
         if self.p2p is None:
             self._X = torch.zeros((n, nfree), **f64)
         self.chisq_cur = torch.zeros(n, **f64)
-        if self.p2p is None or sampler != 'snooker':
+        if self.p2p is None or 'z' not in self.p2p:
             self.Z = torch.zeros((self.zlen, nfree), **f64)
         self.log_post = torch.zeros(self.zlen, **f64)
         self.zchain = torch.full((self.zlen,), -1, dtype=torch.int32, device=self.dev)
@@ -254,6 +255,7 @@ class Population:
         self._plans = {}
         self._work = {}
         self._graph = None
+        self._block_graph = None
         # launch shape planned for `plan_chains` chains instead of the chains of each
         # launch: identical chi-squared bits however the population is spread over
         # launches / devices (include/mc3b200.h, mc3b_chisq_opts_t)
@@ -287,8 +289,10 @@ class Population:
         S.X, S.chisq_cur = self.X.data_ptr(), self.chisq_cur.data_ptr()
         S.world, S.rank = self.world, self.rank
         if self.p2p is not None:
-            S.X_peers = self.p2p['x_ptrs']
-            S.Z_peers = self.p2p.get('z_ptrs')
+            S.X_peers = self.p2p['x'].ptrs.data_ptr()
+            S.F_peers = self.p2p['f'].ptrs.data_ptr()
+            if 'z' in self.p2p:
+                S.Z_peers = self.p2p['z'].ptrs.data_ptr()
         S.Z, S.log_post, S.zchain = (self.Z.data_ptr(), self.log_post.data_ptr(),
                                      self.zchain.data_ptr())
         S.zlen, S.M0 = self.zlen, self.M0
@@ -309,26 +313,29 @@ class Population:
 
     def _setup_p2p(self, n, nfree):
         import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm
-        grp = self.group if self.group is not None else dist.group.WORLD
-        try:
-            symm.enable_symm_mem_for_group(grp.group_name)
-        except Exception:
-            pass
-        self._Xsym = symm.empty((2, n, nfree), dtype=torch.float64, device=self.dev)
+        from .parallel import PeerBuffer
+        grp = self.group
+        args = (self, self.rank, self.world, grp, self.dev)
+        out = {'x': PeerBuffer.get(2*n*nfree*8, 'x', *args),
+               'f': PeerBuffer.get(max(self.world, 8)*8, 'f', *args)}
+        self._Xsym = out['x'].local[:2*n*nfree].view(2, n, nfree)
         self._Xsym.zero_()
-        xh = symm.rendezvous(self._Xsym, grp)
-        out = {'x_hdl': xh, 'x_ptrs': int(xh.buffer_ptrs_dev)}
+        out['f'].local.zero_()
         if self.sampler == 'snooker':
-            self.Z = symm.empty((self.zlen, nfree), dtype=torch.float64, device=self.dev)
+            out['z'] = PeerBuffer.get(self.zlen*nfree*8, 'z', *args)
+            self.Z = out['z'].local[:self.zlen*nfree].view(self.zlen, nfree)
             self.Z.zero_()
-            zh = symm.rendezvous(self.Z, grp)
-            out['z_hdl'] = zh
-            out['z_ptrs'] = int(zh.buffer_ptrs_dev)
         torch.cuda.synchronize(self.dev)
-        xh.barrier(channel=0)                   # nobody stores into a peer before its buffers are zeroed
-        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=grp)                 # nobody stores into a peer before its buffers are zeroed
         return out
+
+    def close(self):
+        """Drop the captured graphs (they may hold NCCL kernels: destroy them before
+        the process group) and release the peer buffers for reuse."""
+        self._graph = None
+        self._block_graph = None
+        if torch.cuda.is_available():
+            torch.cuda.synchronize(self.dev)
 
     def set_jump_scales(self, fgamma, fepsilon):
         self.S.gamma = float(fgamma)*2.38/np.sqrt(2*self.nfree)   # chain.py:175
@@ -435,6 +442,18 @@ class Population:
         return out, nb, 1
 
     @on_device
+    def model_eval(self, fpar):
+        """Built-in model at one parameter vector over the (device-resident)
+        abscissa, as a host array (chain.py:316-319 `func(params, *indparams)`)."""
+        P = torch.as_tensor(np.atleast_2d(np.asarray(fpar, dtype=np.double)), device=self.dev)
+        out = torch.empty((1, self.ndata), dtype=torch.float64, device=self.dev)
+        _lib.call('mc3b_model_eval', self.func.model_id, P.data_ptr(), P.shape[1], 1,
+                  self.nmodel, self.d_x.data_ptr(), self.ndata, out.data_ptr(),
+                  _lib.stream_ptr())
+        self.launches += 1
+        return to_host(out[0])
+
+    @on_device
     def chisq(self, P):
         """chi-squared + prior terms of full parameter vectors P [nb, npars]."""
         P = P.contiguous()
@@ -466,13 +485,20 @@ class Population:
             _lib.call('mc3b_init_trials', ctypes.byref(self.S), kick, nt, rnd,
                       trial.data_ptr(), ok.data_ptr(), _lib.stream_ptr())
             self.launches += 1
-            lp = self._trial_log_post(trial)
-            good = (ok != 0) & torch.isfinite(lp)
-            idx = torch.nonzero(good).flatten()[:M0 - got]
-            rows.append(trial[idx])
-            lps.append(lp[idx])
-            got += idx.numel()
-            tried += nt
+            # Trials are used in draw order until M0 rows are in (mcmc_driver.py:246-262):
+            # evaluate the in-bounds ones up to the count still needed (+1% against
+            # non-finite models), not the whole over-drawn batch.
+            inb = torch.nonzero(ok != 0).flatten()
+            need = M0 - got
+            inb = inb[:need + max(8, need//100)]
+            tried += int(inb[-1]) + 1 if inb.numel() else nt
+            if inb.numel():
+                cand = trial[inb]
+                lp = self._trial_log_post(cand)
+                idx = torch.nonzero(torch.isfinite(lp)).flatten()[:need]
+                rows.append(cand[idx])
+                lps.append(lp[idx])
+                got += idx.numel()
             rnd += 1
         if got < M0:
             raise ValueError(
@@ -511,10 +537,11 @@ class Population:
         self.Z[:self.M0] = Z0
         self.log_post[:self.M0] = lp0
         if self._Xsym is not None:
+            import torch.distributed as dist
             self._Xsym[0].copy_(self.Z[:self.nchains])
             self._Xsym[1].copy_(self.Z[:self.nchains])
             torch.cuda.synchronize(self.dev)    # peers may store into our halves after this barrier only
-            self.p2p['x_hdl'].barrier(channel=0)
+            dist.barrier(group=self.group)
         else:
             self._X.copy_(self.Z[:self.nchains])
         self.chisq_cur.copy_(-2.0*self.log_post[:self.nchains])
@@ -543,17 +570,20 @@ class Population:
         zrow0 = self._zrow0(gen) if gen >= 0 else -1
         # the generation counter may advance inside the fused kernel only when no
         # later launch of this generation reads it
-        exch = self.world > 1 and self.shard == 'chains'
+        # peer mode: the kernel that ends the generation advances the counter and
+        # publishes this device's generation flag (host-driven generations too)
+        nccl = self.world > 1 and self.shard == 'chains' and self.p2p is None
+        adv = (gen < 0 and not nccl) or self.p2p is not None
         if self.fused:
-            self.data_chisq(self.nextp[c0:c1], fuse=(c0, gen, zrow0, gen < 0 and not exch))
+            self.data_chisq(self.nextp[c0:c1], fuse=(c0, gen, zrow0, adv))
         else:
             part, ld, ns = self.data_chisq(self.nextp[c0:c1])
             _lib.call('mc3b_metropolis', ctypes.byref(self.S), part.data_ptr(), ld, ns,
                       c0, gen, zrow0, c0, c1, st)
             self.launches += 1
-        if exch:
+        if nccl:
             self._exchange(gen)
-        if gen < 0 and not (self.fused and not exch):
+        if (adv and not self.fused) or (gen < 0 and nccl):
             _lib.call('mc3b_advance', ctypes.byref(self.S), st)
             self.launches += 1
 
@@ -562,9 +592,6 @@ class Population:
         needs every chain's current state, snooker the new history rows.  Peer
         mode: the stores were issued by k_metropolis; one signal-pad barrier
         orders them.  NCCL mode: all-gather of X (demc) / of the new rows (snooker)."""
-        if self.p2p is not None:
-            self.p2p['x_hdl'].barrier(channel=0)
-            return
         if self.sampler == 'demc':
             allgather_rows(self._X, self.chain0, self.nlocal, self.group)
         elif self.sampler == 'snooker':
@@ -626,6 +653,8 @@ class Population:
             self.gen += ngen
             return
         if not use_graph:
+            if self.p2p is not None:
+                self.gen_dev.fill_(self.gen)     # the device counter advances with every generation
             for g in range(self.gen, self.gen + ngen):
                 self._generation(g)
             self.gen += ngen
@@ -722,8 +751,7 @@ class Population:
             return
         lo = self.M0 + k0*self.nchains
         for t in (self.Z, self.log_post, self.zchain):
-            if t is self.Z and (self.sampler == 'snooker' or
-                                (self.p2p is not None and 'z_hdl' in self.p2p)):
+            if t is self.Z and self.sampler == 'snooker':
                 continue                     # snooker exchanges its rows every generation
             gather_history(t, lo, K - k0, self.nchains, self.rank, self.world,
                            self.group, dst)
@@ -810,7 +838,8 @@ class Population:
         """median, mean, std and central-quantile bounds of the burned posterior,
         per free parameter, computed on the device over the lock-step block of
         rows after burn-in (stats.py:764-802 'med_central'; numpy's linear
-        percentile rule).  Sorting is torch.sort: post-processing, not the hot path."""
+        percentile rule) and fetched with one copy.  Sorting is torch.sort:
+        post-processing, not the hot path."""
         lo, hi = self.M0 + zburn*self.nchains, self.zsize()
         blk = self.Z[lo:hi]
         n = blk.shape[0]
@@ -821,10 +850,10 @@ class Population:
             i0 = int(np.floor(pos))
             i1 = min(i0 + 1, n - 1)
             fr = pos - i0
-            return (srt[i0] + (srt[i1] - srt[i0])*fr).cpu().numpy()
-        return (pct(0.5), blk.mean(dim=0).cpu().numpy(),
-                blk.std(dim=0, unbiased=False).cpu().numpy(),
-                pct(0.5*(1 - quantile)), pct(0.5*(1 + quantile)))
+            return srt[i0] + (srt[i1] - srt[i0])*fr
+        out = torch.stack([pct(0.5), blk.mean(dim=0), blk.std(dim=0, unbiased=False),
+                           pct(0.5*(1 - quantile)), pct(0.5*(1 + quantile))]).cpu().numpy()
+        return tuple(out)
 
     def gelman_rubin_async(self, zburn):
         """PSRF per free parameter over every chain's samples after burn-in

@@ -31,8 +31,8 @@ def eval_model(pop, params, ret='model'):
     if ret == 'chisq':
         return chisq
     fpar = np.asarray(params, float)[:pop.nfunc]
-    if isinstance(pop.func, (BuiltinModel, TorchModel)):
-        model = pop.func(fpar, *pop.indparams, **pop.indparams_dict)
+    if pop.kind == 'builtin' and pop.shard != 'data':
+        model = pop.model_eval(fpar)          # abscissa already on the device
     else:
         model = pop.func(fpar, *pop.indparams, **pop.indparams_dict)
     return (model, chisq) if ret == 'both' else model
@@ -57,9 +57,13 @@ def update_output(output, pop, hsize, counters=None):
     chi-squared column and, for a lock-step history, the burned-sample
     statistics are computed on the device; only results travel to the host."""
     zburn = output['burnin']
-    Z, zchain, log_post, chisq = pop.history_host()
+    root = pop.world == 1 or pop.rank == 0
+    # chains partitioned over devices: only rank 0 receives the other devices'
+    # rows and copies the history to its host
+    dst = 0 if (pop.world > 1 and pop.shard == 'chains') else None
+    Z, zchain, log_post, chisq = pop.history_host(dst)
     c = counters or pop.counters()
-    nsample = zchain.size*pop.thinning
+    nsample = (pop.zsize() - pop.first_valid)*pop.thinning
     output['posterior'] = Z
     output['zchain'] = zchain
     output['chisq'] = chisq
@@ -73,6 +77,8 @@ def update_output(output, pop, hsize, counters=None):
      output['stddev_residuals']) = best
     if not pop.thinned_done() > zburn:
         return None
+    if not root:
+        return (pop.thinned_done() - zburn)*pop.nchains
     if pop.first_valid == pop.M0:          # lock-step layout: closed-form burn mask
         K, n = pop.thinned_done(), pop.nchains
         zmask = (np.arange(zburn, K)[None, :]*n + np.arange(n)[:, None]).ravel()
@@ -94,7 +100,7 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
          fgamma, fepsilon, hsize, kickoff, savefile, resume, log,
          pnames, texnames, seed=None, dtype='f64', device=None, use_graph=None,
          rank=0, world=1, group=None, reflect=False, return_population=False,
-         shard='chains'):
+         shard='chains', plan_chains=None):
     """Reference signature (mcmc_driver.py:18-26; `ncpu` is accepted and
     ignored) plus keyword-only device options."""
     pstep = np.asarray(pstep, float)
@@ -137,7 +143,7 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
         wlike=wlike, fgamma=fgamma, fepsilon=fepsilon, hsize=hsize,
         thinning=thinning, nzchain=nzchain, seed=seed, dtype=dtype,
         device=device, rank=rank, world=world, group=group, reflect=reflect,
-        M0=M0, shard=shard)
+        M0=M0, shard=shard, plan_chains=plan_chains)
 
     if resume:
         _resume(pop, oldrun)
@@ -173,19 +179,21 @@ def mcmc(data, uncert, func, params, indparams, indparams_dict,
             if not block and not (hc[1].query() and (hg is None or hg[1].query())):
                 return False
             pending.pop(0)
-            c = pop.counters_result(hc)
-            log.progressbar(kd/nzchain)
-            log.msg(
-                f"Out-of-bound Trials:\n{c['outbounds']}\n"
-                f"Best Parameters: (chisq={-2*c['best_log_post']:.4f})\n"
-                f"{c['bestp'][ifree]}", width=80)
+            if log.verb >= 2:                # (formatting the arrays costs more than the report)
+                c = pop.counters_result(hc)
+                log.progressbar(kd/nzchain)
+                log.msg(
+                    f"Out-of-bound Trials:\n{c['outbounds']}\n"
+                    f"Best Parameters: (chisq={-2*c['best_log_post']:.4f})\n"
+                    f"{c['bestp'][ifree]}", width=80)
             if hg is not None:
                 hg[1].synchronize()
                 psrf = hg[0].numpy()
-                log.msg(f"Gelman-Rubin statistics for free parameters:\n{psrf}",
-                        width=80)
-                if np.all(psrf < 1.01):
-                    log.msg("All parameters converged to within 1% of unity.")
+                if log.verb >= 2:
+                    log.msg(f"Gelman-Rubin statistics for free parameters:\n{psrf}",
+                            width=80)
+                    if np.all(psrf < 1.01):
+                        log.msg("All parameters converged to within 1% of unity.")
                 if grbreak > 0.0 and np.all(psrf < grbreak) and zs > grnmin:
                     log.msg(
                         "\nAll parameters satisfy the GR convergence "

@@ -10,6 +10,8 @@ What travels, per generation:
 and at report points the thinned history / counters.  Every function here works
 on plain tensors, so the same code runs under gloo on CPU in the tests.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -63,3 +65,58 @@ def sum_owned(t, chain0, nlocal, group=None):
     m[chain0:chain0 + nlocal] = t[chain0:chain0 + nlocal]
     dist.all_reduce(m, group=group)
     return m
+
+
+# ---------------------------------------------------------------------------
+# Peer memory: one buffer per device, mapped into every process of the box
+# ---------------------------------------------------------------------------
+class _RawCuda:
+    """CUDA array interface over memory the C library allocated."""
+    def __init__(self, ptr, nelem, typestr):
+        self.__cuda_array_interface__ = {'shape': (nelem,), 'typestr': typestr,
+                                         'data': (ptr, False), 'version': 2}
+
+
+class PeerBuffer:
+    """`nbytes` of zeroed device memory on every rank of `group`, each mapped into
+    every process with CUDA IPC (mc3b_peer_alloc / mc3b_peer_open).  `local` is this
+    rank's buffer as a float64 tensor; `ptrs` a device int64 tensor of all ranks'
+    addresses in THIS process (what the kernels take as X_peers / Z_peers /
+    F_peers).  Buffers are cached per (group, size, tag): the handle exchange is paid
+    once per process, not once per mcmc() call."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, nbytes, tag, owner, rank, world, group, dev):
+        """A cached buffer no live object owns, else a new one (every rank runs the
+        same program, so every rank takes the same branch)."""
+        import weakref
+        key = (id(group) if group is not None else 0, int(nbytes), tag, dev.index)
+        for pb in cls._cache.setdefault(key, []):
+            if pb.owner is None or pb.owner() is None:
+                pb.owner = weakref.ref(owner)
+                return pb
+        pb = cls(nbytes, rank, world, group, dev)
+        pb.owner = weakref.ref(owner)
+        cls._cache[key].append(pb)
+        return pb
+
+    def __init__(self, nbytes, rank, world, group, dev):
+        from . import _lib
+        nbytes = (int(nbytes) + 255)//256*256
+        ptr = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.call('mc3b_peer_alloc', nbytes, ctypes.byref(ptr), handle)
+        handles = [None]*world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        addrs = []
+        for r in range(world):
+            if r == rank:
+                addrs.append(ptr.value)
+            else:
+                q = ctypes.c_void_p()
+                _lib.call('mc3b_peer_open', handles[r], ctypes.byref(q))
+                addrs.append(q.value)
+        self.nbytes, self.addrs = nbytes, addrs
+        self.local = torch.as_tensor(_RawCuda(ptr.value, nbytes//8, '<f8'), device=dev)
+        self.ptrs = torch.tensor(addrs, dtype=torch.int64, device=dev)

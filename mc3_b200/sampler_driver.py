@@ -170,7 +170,7 @@ def sample(data=None, uncert=None, func=None, params=None,
     if leastsq is not None:                        # :412-440
         fit_output = fit(data, uncert, func, np.copy(params), indparams,
                          indparams_dict, pstep, pmin, pmax, prior, priorlow,
-                         priorup, leastsq)
+                         priorup, leastsq, wlike=wlike)
         log.msg("Least-squares best-fitting parameters:\n"
                 f"  {fit_output['bestp']}\n\n", si=2)
         if chisqscale:
@@ -178,7 +178,7 @@ def sample(data=None, uncert=None, func=None, params=None,
             uncert *= chisq_factor
             fit_output = fit(data, uncert, func, np.copy(params), indparams,
                              indparams_dict, pstep, pmin, pmax, prior, priorlow,
-                             priorup, leastsq)
+                             priorup, leastsq, wlike=wlike)
             log.msg("Least-squares best-fitting parameters (rescaled chisq):"
                     f"\n  {fit_output['bestp']}\n\n", si=2)
         params = np.copy(fit_output['bestp'])
@@ -189,7 +189,8 @@ def sample(data=None, uncert=None, func=None, params=None,
             chisq_factor = float(oldrun['chisq_factor'])
 
     dev_kw = {k: kwargs[k] for k in ('seed', 'dtype', 'device', 'use_graph',
-                                     'reflect', 'rank', 'world', 'group', 'shard')
+                                     'reflect', 'rank', 'world', 'group', 'shard',
+                                     'plan_chains')
               if k in kwargs}
     output = mcmc(
         data, uncert, func, params, indparams, indparams_dict,
@@ -199,6 +200,12 @@ def sample(data=None, uncert=None, func=None, params=None,
         pnames, texnames, **dev_kw)
 
     output['chisq_factor'] = chisq_factor
+    if dev_kw.get('world', 1) > 1 and dev_kw.get('rank', 0) != 0:
+        # chains partitioned over devices: rank 0 holds the gathered history,
+        # computes the posterior statistics and writes the files
+        if closelog:
+            log.close()
+        return output
     if leastsq is not None:
         dlp = output['best_log_post'] - fit_output['best_log_post']
         dpar = output['bestp'] - fit_output['bestp']
@@ -221,7 +228,7 @@ def sample(data=None, uncert=None, func=None, params=None,
         stat_post = posterior[pick]
     else:
         stat_post = np.copy(posterior)
-    st = ms.calc_sample_statistics(stat_post, bestp, pstep, calc_hpd=True)
+    st = ms.calc_sample_statistics(stat_post, bestp, pstep, calc_hpd=True, device=True)
     keys = ('medianp', 'meanp', 'stdp', 'median_low_bounds', 'median_high_bounds',
             'mode', 'hpd_low_bounds', 'hpd_high_bounds')
     for k, v in zip(keys, st):

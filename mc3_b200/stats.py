@@ -18,7 +18,7 @@ from . import _lib
 
 __all__ = ['bin_array', 'residuals', 'chisq', 'dwt_chisq', 'dwt_daub4',
            'time_avg', 'gelman_rubin', 'log_prior', 'cred_region',
-           'marginal_statistics', 'calc_sample_statistics']
+           'marginal_statistics', 'calc_sample_statistics', 'hpd_statistics']
 
 
 def _dev():
@@ -269,6 +269,24 @@ def marginal_statistics(posterior, statistics='med_central', quantile=0.683,
     return values, low, high
 
 
+def hpd_statistics(posterior, quantile=0.683):
+    """mode, hpd_low, hpd_high of every column of posterior [n, nfree] on the GPU
+    (mc3b_hpd): the reference's cred_region + marginal_statistics('max_like',
+    stats.py:433-467, 764-802) -- Gaussian KDE on 100 points, linear resample to
+    3000, density threshold at `quantile`."""
+    post = np.ascontiguousarray(posterior, dtype=np.double)
+    n, nfree = post.shape
+    dP = _up(post)
+    lib = _lib.load()
+    ws = torch.empty(max(lib.mc3b_hpd_workspace(nfree), 8)//8, dtype=torch.float64,
+                     device=dP.device)
+    out = torch.empty((3, nfree), dtype=torch.float64, device=dP.device)
+    _lib.call('mc3b_hpd', dP.data_ptr(), n, nfree, float(quantile), ws.data_ptr(),
+              out.data_ptr(), _lib.stream_ptr())
+    res = out.cpu().numpy()
+    return res[0], res[1], res[2]
+
+
 def expand_free_stats(free_stats, bestp, pstep):
     """Spread per-free-parameter statistics (median, mean, std, low, high[, mode,
     hpd_low, hpd_high]) over the full parameter vector: fixed parameters keep
@@ -287,10 +305,11 @@ def expand_free_stats(free_stats, bestp, pstep):
 
 
 def calc_sample_statistics(posterior, bestp, pstep, quantile=0.683,
-                           calc_hpd=False, pdf=None, xpdf=None):
+                           calc_hpd=False, pdf=None, xpdf=None, device=False):
     """median, mean, std, central bounds (+ mode and HPD bounds), expanded to
     the full parameter vector: fixed parameters keep bestp with zero std,
-    shared ones copy their source (stats.py:876-964)."""
+    shared ones copy their source (stats.py:876-964).  device=True takes the
+    HPD statistics from the GPU (hpd_statistics) instead of scipy."""
     pstep = np.asarray(pstep)
     npars = len(pstep)
     ifree = np.where(pstep > 0)[0]
@@ -307,7 +326,10 @@ def calc_sample_statistics(posterior, bestp, pstep, quantile=0.683,
     res = [expand(med), expand(np.mean(posterior, axis=0)),
            expand(np.std(posterior, axis=0), fill=0.0), expand(mlo), expand(mhi)]
     if calc_hpd:
-        mode, hlo, hhi = marginal_statistics(posterior, 'max_like', quantile,
-                                             pdf=pdf, xpdf=xpdf)
+        if device and pdf is None and xpdf is None:
+            mode, hlo, hhi = hpd_statistics(posterior, quantile)
+        else:
+            mode, hlo, hhi = marginal_statistics(posterior, 'max_like', quantile,
+                                                 pdf=pdf, xpdf=xpdf)
         res += [expand(mode), expand(hlo), expand(hhi)]
     return tuple(res)

@@ -26,17 +26,56 @@ def config2(n=100_000, seed=20260102):
         flops_per_point=10)        # model 7 + residual/square 3
 
 
+def inverse_daub4(coef):
+    """Inverse Daubechies-4 pyramid of a length-2^M coefficient vector laid out as
+    the reference's transform leaves it (wavelet.h:109-128: two smooth coefficients,
+    then 2^m details of scale m at [2^m, 2^(m+1))).  Vectorised numpy, used only to
+    synthesise red noise for config 3; the product transform is
+    mc3b_daub4."""
+    c0, c1 = (1 + np.sqrt(3))/(4*np.sqrt(2)), (3 + np.sqrt(3))/(4*np.sqrt(2))
+    c2, c3 = (3 - np.sqrt(3))/(4*np.sqrt(2)), (1 - np.sqrt(3))/(4*np.sqrt(2))
+    a = np.array(coef, dtype=float)
+    n = a.size
+    nn = 4
+    while nn <= n:
+        nh = nn//2
+        s, d = a[:nh].copy(), a[nh:nn].copy()
+        sp, dp = np.roll(s, 1), np.roll(d, 1)            # element i-1, periodic
+        a[0:nn:2] = c2*sp + c1*dp + c0*s + c3*d
+        a[1:nn:2] = c3*sp - c0*dp + c1*s - c2*d
+        nn *= 2
+    return a
+
+
+def red_noise(n, sigma_r, gamma=1.0, rs=None):
+    """1/f^gamma noise of Carter & Winn (2009) as the wavelet likelihood models it:
+    independent wavelet coefficients with variance sigma_r^2 2^(-gamma m) at scale m
+    and sigma_r^2 2^(-gamma) g(gamma) for the two scaling coefficients (_dwt.c:96-110),
+    taken back to the time domain."""
+    rs = rs or np.random.RandomState(0)
+    M = int(np.log2(n))
+    assert 1 << M == n
+    g = 0.72134752 if gamma == 1.0 else 1.0/(2.0**(1.0 - gamma) - 1.0)
+    c = np.empty(n)
+    c[0:2] = rs.normal(0, sigma_r*np.sqrt(2.0**(-gamma)*g), 2)
+    for m in range(1, M):
+        c[1 << m:1 << (m + 1)] = rs.normal(0, sigma_r*2.0**(-0.5*gamma*m), 1 << m)
+    return inverse_daub4(c)
+
+
 def config3(n=1 << 20, seed=20260103):
-    """snooker, transit-like box, N=2^20, wavelet likelihood."""
+    """snooker, transit-like box, N=2^20, wavelet likelihood: white noise
+    sigma_w = 1e-3 plus red noise sigma_r = 5e-3 synthesised by the inverse D4
+    transform."""
     rs = np.random.RandomState(seed)
     x = np.linspace(-0.5, 0.5, n)
     ptrue = np.array([0.01, 0.0, 0.1, 1.0])
     y = ptrue[3] - ptrue[0]*(np.abs(x - ptrue[1]) < 0.5*ptrue[2])
-    data = y + rs.normal(0, 1e-3, n)
+    data = y + rs.normal(0, 1e-3, n) + red_noise(n, 5e-3, 1.0, rs)
     return dict(
-        name='config3: snooker, box light curve N=2^20, wlike',
+        name='config3: snooker, box light curve N=2^20, wlike, white + red (inverse D4) noise',
         model='box', x=x, data=data, uncert=np.full(n, 1e-3),
-        params=np.array([0.0101, 0.001, 0.1003, 1.0, 1.0, 5e-4, 1e-3]),
+        params=np.array([0.0101, 0.001, 0.1003, 1.0, 1.0, 5e-3, 1e-3]),
         pstep=np.array([2e-4, 1e-3, 1e-3, 1e-4, 0.0, 1e-4, 5e-5]),
         pmin=np.array([0.0, -0.2, 0.01, 0.9, 0.0, 1e-5, 1e-4]),
         pmax=np.array([0.05, 0.2, 0.3, 1.1, 2.0, 1e-2, 1e-2]),

@@ -157,14 +157,31 @@ def mcmc_golden(R):
                   f'oob={b["outbounds"].tolist()}')
 
 
+def hpd_golden(R):
+    """Reference calc_sample_statistics(calc_hpd=True) (stats.py:876-964, scipy KDE)
+    on the seeded posterior of problems.hpd_case, at two quantiles."""
+    post, bestp, pstep = pb.hpd_case()
+    g = {'in_checksum': pb.checksum(post, bestp, pstep)}
+    for q in (0.683, 0.9545):
+        st = R.stats.calc_sample_statistics(post, bestp, pstep, quantile=q, calc_hpd=True)
+        for name, v in zip(('median', 'mean', 'std', 'med_lo', 'med_hi', 'mode', 'hpd_lo', 'hpd_hi'), st):
+            g[f'{name}_{q}'] = v
+    np.savez(os.path.join(GOLD, 'hpd.npz'), **g)
+    print('hpd.npz:', len(g), 'entries')
+
+
 def main():
     if not ref.have_ref_py():
         sys.exit('make_golden needs /root/reference (authoring container only)')
     ok.build()
     R = ref.ref_py()
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == 'hpd':
+        hpd_golden(R)
+        return
     kernels_golden(R)
     mcmc_golden(R)
+    hpd_golden(R)
 
 
 if __name__ == '__main__':

@@ -184,3 +184,18 @@ KAT_RED_RMSHI = [0.11639013, 0.12995296, 0.1285489, 0.13412548, 0.15774034,
              0.24306181, 0.23335404, 0.25645724, 0.29446565, 0.26262799]
 
 
+
+
+def hpd_case(n=20000, seed=77):
+    """Posterior sample [n, 4] for the HPD golden (tests/golden/hpd.npz): a Gaussian,
+    a skewed (log-normal), a bimodal and a bounded (half-normal) marginal; 5
+    parameters with one fixed and one shared entry in pstep."""
+    rs = np.random.RandomState(seed)
+    g = rs.normal(3.0, 0.2, n)
+    ln = np.exp(rs.normal(0.0, 0.5, n))
+    bi = np.where(rs.uniform(size=n) < 0.35, rs.normal(-1.0, 0.3, n), rs.normal(1.5, 0.5, n))
+    hn = np.abs(rs.normal(0.0, 1.0, n))
+    post = np.column_stack([g, ln, bi, hn])
+    pstep = np.array([0.1, 0.1, 0.0, 0.1, -1.0, 0.1])
+    bestp = np.array([3.0, 1.0, 7.0, 1.4, 3.0, 0.1])
+    return post, bestp, pstep

@@ -41,4 +41,5 @@ def hub():
 hub(); sync()
 t0 = time.perf_counter(); hub(); sync(); print('mcmc() warm wall', 1e3*(time.perf_counter()-t0), 'ms')
 pr = cProfile.Profile(); pr.enable(); hub(); sync(); pr.disable()
-pstats.Stats(pr).sort_stats('cumulative').print_stats(22)
+pstats.Stats(pr).sort_stats('cumulative').print_stats(45)
+pstats.Stats(pr).sort_stats('tottime').print_stats(25)

@@ -50,6 +50,26 @@ def _worker(rank, world, port, q):
         want = torch.cat([torch.full((M0,), -1, dtype=torch.int32),
                           torch.arange(nchains, dtype=torch.int32).repeat(K)])
         ok_c = torch.equal(zc, want)
+        # history gather to rank 0 only, in two instalments (rows [0, 3) then [3, 5))
+        Z2 = torch.zeros_like(truth)
+        Z2[:M0] = truth[:M0]
+        for k in range(K):
+            r = M0 + k*nchains + c0
+            Z2[r:r + nl] = truth[r:r + nl]
+        mine_before = Z2.clone()
+        par.gather_history(Z2, M0, 3, nchains, rank, world, dst=0)
+        par.gather_history(Z2, M0 + 3*nchains, K - 3, nchains, rank, world, dst=0)
+        ok_z = ok_z and (torch.equal(Z2, truth) if rank == 0 else torch.equal(Z2, mine_before))
+        # packed report counters: one row per rank, combined on the host
+        # (what Population.counters_async all-gathers; layout of mc3b_pack_counters)
+        nf = 3
+        row = torch.tensor([10.0 + rank, 5.0 - rank, 7.0, float(c0 + 1)] +
+                           [float(rank)]*nf + [1.0, 2.0, 3.0 + rank], dtype=torch.float64)
+        parts = [torch.empty_like(row) for _ in range(world)]
+        dist.all_gather(parts, row)
+        h = torch.stack(parts).numpy()
+        ok_z = ok_z and h[:, 0].sum() == 21.0 and h[:, 4 + nf:].sum(axis=0).tolist() == [2.0, 4.0, 7.0] \
+            and min(h, key=lambda r: (r[1], r[2], r[3]))[3] == 5.0
         # owned-slice reduction
         acc = torch.zeros(nchains, dtype=torch.int32)
         acc[c0:c0 + nl] = rank + 1

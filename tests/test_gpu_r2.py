@@ -261,3 +261,28 @@ def test_device_keyword_selects_the_gpu(mc3):
     b = mc3.sample(**kw, device='cuda:1')
     assert torch.cuda.current_device() == 0
     assert np.array_equal(a['posterior'], b['posterior'])
+
+
+def test_hpd_statistics_on_device_match_reference_golden(mc3):
+    """mc3b_hpd (device KDE on 100 points, 3000-point resample, descending running
+    sum) against the reference's calc_sample_statistics(calc_hpd=True) on the seeded
+    posterior of problems.hpd_case: Gaussian, skewed, bimodal and bounded marginals,
+    two quantiles; rtol 1e-6 (scipy's KDE sums in another order)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hpd.npz'))
+    post, bestp, pstep = pb.hpd_case()
+    assert str(g['in_checksum']) == pb.checksum(post, bestp, pstep)
+    for q in (0.683, 0.9545):
+        st = mc3.stats.calc_sample_statistics(post, bestp, pstep, quantile=q, calc_hpd=True, device=True)
+        for name, v in zip(('median', 'mean', 'std', 'med_lo', 'med_hi', 'mode', 'hpd_lo', 'hpd_hi'), st):
+            np.testing.assert_allclose(v, g[f'{name}_{q}'], rtol=1e-6, atol=1e-9, err_msg=f'{name} q={q}')
+    # more samples than the KDE keeps (every n/120000-th): thinning path
+    rs = np.random.RandomState(3)
+    big = rs.normal(1.0, 2.0, (250000, 2))
+    big[:, 1] = np.exp(0.3*big[:, 1])
+    mode, lo, hi = mc3.stats.hpd_statistics(big, 0.683)
+    for i in range(2):
+        pdf, xpdf, hmin = mc3.stats.cred_region(big[:, i], 0.683)
+        sel = xpdf[pdf > hmin]
+        np.testing.assert_allclose([mode[i], lo[i], hi[i]], [xpdf[np.argmax(pdf)], sel.min(), sel.max()],
+                                   rtol=1e-6, atol=1e-9)

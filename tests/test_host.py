@@ -124,3 +124,39 @@ def test_log_prior_doc_values():
     lp = ms.log_prior(post, np.array([3.5, 0.0]), np.array([0.1, 0.0]),
                       np.array([0.1, 0.0]), np.array([1.0, 1.0]))
     np.testing.assert_allclose(lp, [-12.5, -8.0, -0.5])
+
+
+def test_config3_red_noise_generator_matches_oracle_transform():
+    """workloads.inverse_daub4 (used to synthesise config 3's red noise)
+    is the reference's inverse D4 pyramid; the noise has the 1/f scale variances."""
+    import numpy as np
+    from mc3_b200 import workloads
+    from oracle import kernels as ok
+    rs = np.random.RandomState(5)
+    for n in (4, 8, 64, 1024):
+        c = rs.normal(0, 1, n)
+        np.testing.assert_allclose(workloads.inverse_daub4(c), ok.dwt_daub4(c, True), rtol=0, atol=1e-15)
+    r = workloads.red_noise(1 << 14, 5e-3, 1.0, np.random.RandomState(1))
+    coef = ok.dwt_daub4(r)
+    for m in (6, 9, 12):                              # scale variances sigma_r^2 2^-m
+        got = np.var(coef[1 << m:1 << (m + 1)])
+        assert abs(got/(5e-3**2*2.0**-m) - 1) < 0.35
+    w = workloads.config3(n=1 << 12)
+    assert w['data'].size == 1 << 12 and w['params'][5] == 5e-3
+
+
+def test_sample_statistics_host_path_matches_reference_golden():
+    """calc_sample_statistics (host numpy/scipy path) against the reference's own
+    output on the seeded posterior of problems.hpd_case (tests/golden/hpd.npz,
+    written by oracle/make_golden.py from mc3/stats/stats.py:876-964)."""
+    import os
+    import numpy as np
+    from mc3_b200 import stats as ms
+    from oracle import problems as pb
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'hpd.npz'))
+    post, bestp, pstep = pb.hpd_case()
+    assert str(g['in_checksum']) == pb.checksum(post, bestp, pstep)
+    for q in (0.683, 0.9545):
+        st = ms.calc_sample_statistics(post, bestp, pstep, quantile=q, calc_hpd=True)
+        for name, v in zip(('median', 'mean', 'std', 'med_lo', 'med_hi', 'mode', 'hpd_lo', 'hpd_hi'), st):
+            np.testing.assert_allclose(v, g[f'{name}_{q}'], rtol=1e-9, atol=1e-12, err_msg=name)
