@@ -135,52 +135,89 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------
-# CPU reference arm / baseline: oracle port of the reference loop
+# CPU reference arm / baseline: the reference's own mcmc() on the host cores
 # --------------------------------------------------------------------------
 def _cpu_worker(args):
+    """One process = one reference run: mc3.mcmc_driver.mcmc() itself (unmodified,
+    byte-compiled by `make -C oracle refpy` into oracle/_ref, with the reference's C
+    chi-squared from oracle/_ref) on 7 chains of config 2, ncpu=1 -- the reference's
+    DEMC dead-locks with ncpu > 1 (SURVEY finding 5), so the host cores are filled
+    with independent runs.  Falls back to the oracle port of the loop when the
+    reference is not staged (kind 'port')."""
     seed, nchains, gens, warm = args
+    os.dup2(2, 1)                                # the reference prints its greeting on stdout
+    import random
     import numpy as np
-    from oracle import mcmc as omc
     from oracle import models as om
-    from oracle import kernels as ok
     from oracle import ref
     from mc3_b200 import workloads
     w = workloads.config2()
-    chisq_fn, kind = ok.chisq, 'port'
-    if ref.have_ref_ext():
-        cs = ref.ref_ext()[0]
+    if ref.have_ref_py() and ref.have_ref_ext():
+        R = ref.ref_py()
+        log = R.utils.Log(verb=0)
 
-        def chisq_fn(model, data, uncert, params, prior, plo, pup):   # stats.py:208-216
-            ip = (plo > 0) & (pup > 0)
-            return cs.chisq(model, data, uncert, (params - prior)[ip], plo[ip], pup[ip])
-        kind = 'reference-chisq'
-    kw = dict(nchains=nchains, sampler='demc', thinning=1, fepsilon=w['fepsilon'],
-              hsize=2, record=False, chisq_fn=chisq_fn, parent_seed=seed,
-              child_seed=seed + 1)
-    args = (w['data'], w['uncert'], om.sinusoid, w['params'], [w['x']], {},
-            w['pmin'], w['pmax'], w['pstep'], w['prior'], w['priorlow'], w['priorup'])
+        def run(ngen):
+            random.randint = lambda a, b: seed + 1           # child seed, chain.py:180
+            np.random.seed(seed)
+            return R.mcmc_driver.mcmc(
+                w['data'], np.copy(w['uncert']), om.sinusoid, np.copy(w['params']), [w['x']], {},
+                w['pmin'], w['pmax'], w['pstep'], w['prior'], w['priorlow'], w['priorup'],
+                nchains, 1, nchains*ngen, 'demc', False, None, False, 0.0, 0.5, 0, 1, 1.0,
+                w['fepsilon'], 2, 'normal', None, False, log, None, None)
+        kind = 'reference'
+    else:
+        from oracle import mcmc as omc
+        from oracle import kernels as ok
+        kw = dict(nchains=nchains, sampler='demc', thinning=1, fepsilon=w['fepsilon'],
+                  hsize=2, record=False, chisq_fn=ok.chisq, parent_seed=seed, child_seed=seed + 1)
+        a = (w['data'], w['uncert'], om.sinusoid, w['params'], [w['x']], {},
+             w['pmin'], w['pmax'], w['pstep'], w['prior'], w['priorlow'], w['priorup'])
+
+        def run(ngen):
+            return omc.mcmc(*a, nsamples=nchains*ngen, **kw)
+        kind = 'port'
     t_setup0 = time.perf_counter()
-    omc.mcmc(*args, nsamples=nchains*max(warm, 1), **kw)       # warm-up + setup cost
+    run(max(warm, 1))                            # warm-up + setup cost (initial population, forks)
     t_setup = time.perf_counter() - t_setup0
     t0 = time.perf_counter()
-    omc.mcmc(*args, nsamples=nchains*(gens + max(warm, 1)), **kw)
+    run(gens + max(warm, 1))
     t_all = time.perf_counter() - t0
     return max(t_all - t_setup, 1e-9), kind
 
 
+def _cpu_proc(args, q):
+    q.put(_cpu_worker(args))
+
+
 def cpu_reference_run(steps, warmup, cores=None):
     """Time `steps` generations of `cores` independent 7-chain DEMC populations
-    (one process each, the reference's own default chain count) at N=1e5."""
+    (one process each, the reference's own default chain count) at N=1e5.  Plain
+    (non-daemonic) processes that exit normally: the reference forks its own chain
+    process, and exit hooks get to run."""
     import multiprocessing as mp
     cores = cores or max(1, (os.cpu_count() or 2) - 1)      # sampler_driver.py:336-341
     ctx = mp.get_context('spawn')
-    with ctx.Pool(cores) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(1000 + 7*i, 7, steps, warmup) for i in range(cores)])
-        wall = time.perf_counter() - t0
+    q = ctx.Queue()
+    t0 = time.perf_counter()
+    procs = [ctx.Process(target=_cpu_proc, args=((1000 + 7*i, 7, steps, warmup), q), daemon=False)
+             for i in range(cores)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=3000) for _ in procs]
+    for p in procs:
+        p.join(60)
+    wall = time.perf_counter() - t0
     tmax = max(r[0] for r in res)
     return dict(value=cores*7*steps/tmax, seconds=tmax, wall=wall, cores=cores,
                 kind=res[0][1], chain_steps=cores*7*steps)
+
+
+def _cpu_sample_text(r, steps):
+    how = ('the UNMODIFIED reference mc3.mcmc_driver.mcmc() (byte-compiled into oracle/_ref, ncpu=1 '
+           'per run: its DEMC dead-locks with ncpu > 1) with the reference C chi-squared'
+           if r['kind'] == 'reference' else 'the oracle port of mc3/chain.py with the oracle C chi-squared')
+    return (f'{r["cores"]} independent processes x 7 chains x {steps} generations of config 2 '
+            f'(N=1e5, numpy sinusoid model) through {how}; {r["seconds"]:.1f} s')
 
 
 def run_reference(args):
@@ -189,10 +226,6 @@ def run_reference(args):
         return
     K, W = args.steps, args.warmup
     r = cpu_reference_run(K, W)
-    kind = 'port'
-    sample = (f'{r["cores"]} independent processes x 7 chains x {K} generations of config 2 '
-              f'(N=1e5, numpy sinusoid model) with the oracle port of mc3/chain.py; '
-              f'chi-squared by {"the reference C extension (oracle/_ref)" if r["kind"] != "port" else "the oracle C port"}')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': METRIC,
         'n_gpus': args.gpus, 'steps': K, 'warmup': W,
@@ -201,7 +234,7 @@ def run_reference(args):
         'config': {'workload': 'config2: DEMC, 5-param sinusoid+line, N=1e5, fp64 chisq + Gaussian priors',
                    'nchains': r['cores']*7, 'ndata': 100000, 'sampler': 'demc'},
         'cpu_baseline': {'value': r['value'], 'unit': METRIC, 'cores': r['cores'],
-                         'kind': kind, 'sample': sample},
+                         'kind': r['kind'], 'sample': _cpu_sample_text(r, K)},
         'e2e': {'value': r['value'], 'unit': METRIC, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'chisq_evals_per_s': r['value']*100000,
@@ -258,8 +291,14 @@ def run_ours(args):
           for _ in range(K)]
     launches0 = pop.launches
     barrier()
+    align = torch.zeros(1, device=dev)
     for k in range(K):
         flush.fill_(k & 0xFF)                    # evict L2 between timed steps (untimed)
+        if world > 1:
+            # the generations of the devices are coupled (a proposal waits for every
+            # device's previous generation): line the devices up after the untimed flush,
+            # or its skew would be charged to the timed generation of the faster device
+            dist.all_reduce(align)
         ev[k][0].record()
         pop.run(1, use_graph=True)
         ev[k][1].record()
@@ -381,12 +420,8 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_reference_run(args.cpu_steps, 1)
-        cpu = {'value': r['value'], 'unit': METRIC, 'cores': r['cores'], 'kind': 'port',
-               'sample': f'{r["cores"]} processes x 7 chains x {args.cpu_steps} generations '
-                         f'of the same workload (N=1e5) with the oracle port of the '
-                         f'reference loop, numpy model, chi-squared by '
-                         f'{"oracle/_ref (reference C)" if r["kind"] != "port" else "oracle C port"}; '
-                         f'{r["seconds"]:.1f} s'}
+        cpu = {'value': r['value'], 'unit': METRIC, 'cores': r['cores'], 'kind': r['kind'],
+               'sample': _cpu_sample_text(r, args.cpu_steps)}
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': METRIC, 'n_gpus': world,

@@ -221,13 +221,20 @@ def config1(args):
 
 
 def config5(args):
-    """MRW + DEMC, 65536 chains over the GPUs of one box, N = 1e6 points per GPU
-    (launch under torchrun).  --shard chains: chains partitioned, data replicated,
-    population all-gather;  --shard data: data sharded, chi-squared all-gather."""
+    """MRW + DEMC, 65536 chains over the GPUs of one box (launch under torchrun), with
+    the Gelman-Rubin test on the device every 10 generations.
+      --shard chains: chains partitioned, data replicated, population exchange
+      --shard data:   data sharded, chi-squared all-gather, proposals replicated
+      --scaling weak:   N = --n5 points PER GPU (BASELINE config 5: 1e6), so the work
+                        per GPU (65536 x 1e6 chain-points per generation) is fixed
+      --scaling strong: N = --n5 points in TOTAL, fixed problem
+    One JSON line: per-sampler device-timed throughput (CUDA events, max over ranks),
+    the model kernel timed alone against the FP64 FMA peak, and on rank 0 a bounded CPU
+    sample of the same chain-step (numpy model + oracle C chi-squared)."""
     import torch
     import torch.distributed as dist
     import mc3_b200 as mc3
-    from mc3_b200 import workloads
+    from mc3_b200 import _lib, workloads
     from mc3_b200.engine import Population
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -236,60 +243,103 @@ def config5(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    n_total = args.n5*world
+    n_total = args.n5*world if args.scaling == 'weak' else args.n5
     w = workloads.config2(n=n_total, seed=20260105)
-    w['x'] = np.linspace(0, 10.0*world, n_total)
+    w['x'] = np.linspace(0, 10.0*n_total/1e6, n_total)
     w['data'] = workloads.sinusoid_np(np.array([1.0, 2.5, 0.3, 5.0, -0.2]), w['x']) + \
         np.random.RandomState(20260105).normal(0, 0.5, n_total)
     K = args.steps
     lines = []
+    roof = None
     for sampler in ('mrw', 'demc'):
         pop = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {},
                          w['pstep'], w['pmin'], w['pmax'], w['prior'], w['priorlow'], w['priorup'],
                          nchains=args.chains5, sampler=sampler, fepsilon=0.01, thinning=1,
                          nzchain=K + 4, seed=9, hsize=args.hsize, rank=rank, world=world,
                          shard=args.shard)
+        t0 = time.perf_counter()
         pop.init_population('normal')
+        torch.cuda.synchronize()
+        t_init = time.perf_counter() - t0
         pop.run(3)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        pop.run(K)
+        done, psrf_h = 0, []
+        while done < K:                              # Gelman-Rubin on the device every 10 generations
+            step = min(10, K - done)
+            pop.run(step)
+            done += step
+            psrf_h.append(pop.gelman_rubin_async(0))
         b.record()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        psrf = pop.gelman_rubin(0)
+        psrf = psrf_h[-1][0].numpy() if psrf_h[-1] is not None else np.zeros(pop.nfree)
         c = pop.counters()
+        if roof is None:
+            P = pop.nextp[pop.chain0:pop.chain0 + pop.nlocal]
+            kms, _ = timed(torch, lambda: pop._data_chisq_local(P), reps=5, warm=1)
+            peak = fp64_peak(torch, _lib)
+            flops = float(w['flops_per_point'])*pop.nlocal*pop.ndata
+            roof = {'bound': 'fp64', 'kernel': 'k_sinegrid<USIG=true>' if pop.usig and pop.grid else 'k_model_chisq',
+                    'achieved': flops/(kms*1e-3)/1e12, 'peak': peak/1e12, 'unit': 'TFLOP/s',
+                    'frac': flops/(kms*1e-3)/peak, 'ms_per_launch': kms,
+                    'chains_per_launch': pop.nlocal, 'points_per_launch': pop.ndata,
+                    'algorithmic_flops_per_chain_point': w['flops_per_point'],
+                    'hbm_stream_GBs': 8.0*pop.ndata/(kms*1e-3)/1e9}
         lines.append({'sampler': sampler, 'ms_per_step': ms/K,
                       'chain_steps_per_s': args.chains5*K/(ms*1e-3),
                       'chisq_evals_per_s': args.chains5*K/(ms*1e-3)*n_total,
+                      'init_population_s': t_init,
+                      'exchange': ('none (independent chains)' if sampler == 'mrw' and args.shard == 'chains'
+                                   else 'chi-squared all-gather' if args.shard == 'data' and world > 1
+                                   else 'peer-memory stores + generation flags' if pop.p2p is not None
+                                   else 'NCCL all-gather' if world > 1 else 'single GPU'),
                       'acceptance_pct': 100.0*c['numaccept']/(args.chains5*(K + 3)),
-                      'gelman_rubin_max': float(np.max(psrf))})
+                      'gelman_rubin_every': 10, 'gelman_rubin_max': float(np.max(psrf))})
+        pop.close()
         del pop
         torch.cuda.empty_cache()
+    cpu = None
     if rank == 0:
-        print(json.dumps({'metric': 'chain-steps/s', 'n_gpus': world, 'shard': args.shard,
-                          'config': {'workload': 'config5: 65536 chains, sinusoid+line, '
-                                     f'N={args.n5:.0e} points per GPU ({n_total:.0e} total)',
+        from oracle import kernels as ok, models as om
+        ns = min(n_total, 1_000_000)
+        xs, ds, us = w['x'][:ns], w['data'][:ns], w['uncert'][:ns]
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < 5.0:
+            ok.chisq(om.sinusoid(w['params'], xs), ds, us, w['params'], w['prior'], w['priorlow'], w['priorup'])
+            reps += 1
+        per = (time.perf_counter() - t0)/reps*(n_total/ns)
+        cpu = {'value': 1.0/per, 'unit': 'chain-steps/s', 'cores': 1, 'kind': 'port',
+               'sample': f'{reps} chain-steps of numpy sinusoid + oracle C chi-squared on {ns} points '
+                         f'(scaled linearly to N={n_total}): {1e3*per:.1f} ms per chain-step'}
+        print(json.dumps({'metric': 'chain-steps/s', 'unit': 'chain-steps/s',
+                          'value': max(r['chain_steps_per_s'] for r in lines),
+                          'n_gpus': world, 'shard': args.shard, 'scaling': args.scaling, 'dtype': 'f64',
+                          'data': 'synthetic',
+                          'config': {'workload': 'config5: MRW + DEMC, 65536 chains, sinusoid+line, '
+                                     f'N={n_total:.0e} points in total ({n_total//world:.0e} per GPU), '
+                                     'Gelman-Rubin on device every 10 generations',
                                      'nchains': args.chains5, 'ndata_total': n_total,
                                      'hsize': args.hsize, 'steps': K},
-                          'runs': lines}), flush=True)
+                          'runs': lines, 'roofline': roof, 'cpu_baseline': cpu}), flush=True)
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('which', choices=['config1', 'config3', 'config4', 'config5'])
     ap.add_argument('--shard', default='chains', choices=['chains', 'data'])
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--chains5', type=int, default=65536)
     ap.add_argument('--n5', type=int, default=1_000_000)
     ap.add_argument('--chains', type=int, default=16384)

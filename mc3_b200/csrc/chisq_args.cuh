@@ -84,7 +84,26 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    __shared__ double vbuf[STAGE_DOUBLES];
     if (threadIdx.x == 0) sS = f.S;                // constant bank -> shared, static offsets only
+    __syncthreads();
+    if (threadIdx.x < 32) {                        // one warp stages the per-parameter vectors
+        mc3b_sampler_t T = sS;
+        const int np = T.npars, nf = T.nfree;
+        const double* src[7] = {T.pstep, T.pmin, T.pmax, T.params0, T.prior, T.priorlow, T.priorup};
+        for (int i = threadIdx.x; i < 7 * np; i += 32) {
+            const int v = i / np, k = i - v * np;
+            if (src[v]) vbuf[v * MAXP + k] = src[v][k];
+        }
+        int32_t* ifr = reinterpret_cast<int32_t*>(vbuf + 7 * MAXP);
+        for (int i = threadIdx.x; i < nf; i += 32) ifr[i] = T.ifree[i];
+        __syncwarp();
+        if (threadIdx.x == 0) {
+            sS.pstep = vbuf; sS.pmin = vbuf + MAXP; sS.pmax = vbuf + 2 * MAXP; sS.params0 = vbuf + 3 * MAXP;
+            if (T.prior) { sS.prior = vbuf + 4 * MAXP; sS.priorlow = vbuf + 5 * MAXP; sS.priorup = vbuf + 6 * MAXP; }
+            sS.ifree = ifr;
+        }
+    }
     __syncthreads();
     const int64_t cl = (int64_t)blockIdx.x * chains_per_cta + threadIdx.x;
     if ((int)threadIdx.x < chains_per_cta && cl < nchains)

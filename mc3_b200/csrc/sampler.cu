@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(128) k_propose(mc3b_sampler_t S, mc3b_draws_t 
         gen = *S.gen_dev;
         zsize = S.M0 + (gen / S.thinning) * S.nchains;
     }
+    __shared__ double vbuf[STAGE_DOUBLES];
+    stage_vectors(S, vbuf);
     if (!REPLAY && S.F_peers) flags_wait(S, gen);    // every device has finished generation gen-1
     if (c >= c_end) return;
     propose_chain<REPLAY>(S, D, gen, zsize, c);
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(128) k_metropolis(mc3b_sampler_t S, const doub
                                                     int64_t c_off, int64_t gen, int64_t zrow0, int64_t c_begin,
                                                     int64_t c_end) {
     const int64_t c = c_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double vbuf[STAGE_DOUBLES];
+    stage_vectors(S, vbuf);
     if (c >= c_end) return;
     if (gen < 0) {                                   // device-driven generation (graph mode)
         gen = *S.gen_dev;

@@ -39,6 +39,26 @@ __device__ __forceinline__ void flags_wait(const mc3b_sampler_t& S, int64_t gen)
     __syncthreads();
 }
 
+// The per-parameter vectors a chain walks in loops (bounds, steps, priors, free
+// indices) staged in shared memory by the whole CTA in one round of loads, and the
+// sampler description repointed to them: a thread per chain otherwise pays a
+// chain of dependent L2 latencies per parameter.  buf: STAGE_DOUBLES doubles.
+constexpr int STAGE_DOUBLES = 7 * MAXP + MAXP / 2;
+__device__ __forceinline__ void stage_vectors(mc3b_sampler_t& S, double* buf) {
+    const int np = S.npars, nf = S.nfree;
+    const double* src[7] = {S.pstep, S.pmin, S.pmax, S.params0, S.prior, S.priorlow, S.priorup};
+    for (int i = threadIdx.x; i < 7 * np; i += blockDim.x) {
+        const int v = i / np, k = i - v * np;
+        if (src[v]) buf[v * MAXP + k] = src[v][k];
+    }
+    int32_t* ifr = reinterpret_cast<int32_t*>(buf + 7 * MAXP);
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) ifr[i] = S.ifree[i];
+    __syncthreads();
+    S.pstep = buf; S.pmin = buf + MAXP; S.pmax = buf + 2 * MAXP; S.params0 = buf + 3 * MAXP;
+    if (S.prior) { S.prior = buf + 4 * MAXP; S.priorlow = buf + 5 * MAXP; S.priorup = buf + 6 * MAXP; }
+    S.ifree = ifr;
+}
+
 // Proposal of chain c for generation gen (chain.py:185-247, 251-255).
 template <bool REPLAY>
 __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,
@@ -167,7 +187,14 @@ __device__ __forceinline__ double sum_partials(const double* partial, int64_t ld
     double nxt = 0.0;
     const double* p = partial + col;
     int s = 0;
-    for (; s + 8 <= nsplit; s += 8) {               // eight loads in flight, added in order
+    for (; s + 32 <= nsplit; s += 32) {             // 32 loads in flight (the rows come from L2), added in order
+        double v[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) v[k] = CG ? __ldcg(p + (int64_t)(s + k) * ldpartial) : p[(int64_t)(s + k) * ldpartial];
+#pragma unroll
+        for (int k = 0; k < 32; k++) nxt += v[k];
+    }
+    for (; s + 8 <= nsplit; s += 8) {
         double v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = CG ? __ldcg(p + (int64_t)(s + k) * ldpartial) : p[(int64_t)(s + k) * ldpartial];

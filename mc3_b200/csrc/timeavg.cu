@@ -13,6 +13,7 @@
 //
 // binarray: HBM-bound streaming; one warp per bin with coalesced loads (measured
 // faster than shared-memory staging, plain or TMA: see profiles/).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -117,6 +118,47 @@ __global__ void __launch_bounds__(256) k_std(const double* dev, int64_t nblk, in
     if (threadIdx.x == 0) stat[1] = sqrt(a / (double)n);
 }
 
+// One streaming pass for the mean and the population standard deviation when no
+// prefix is needed (every bin size fits the tile kernel): per block of PB points its
+// sum and its squared deviations about ITS OWN mean (two sweeps over registers), then
+// k_moments_finish combines the blocks exactly,
+//   mean = sum_b s_b / n,   M2 = sum_b [ M2_b + n_b (mean_b - mean)^2 ],
+// which is as accurate as the reference's two passes over the data (stats.h:60-72)
+// at half the traffic.
+__global__ void __launch_bounds__(256) k_moments(const double* __restrict__ x, int64_t n, double* tot, double* dev) {
+    __shared__ double sh[9];
+    const int64_t base = (int64_t)blockIdx.x * PB + threadIdx.x * 4;
+    double v[4];
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { const bool in = base + k < n; v[k] = in ? x[base + k] : 0.0; cnt += in; }
+    const double s = block_sum_256((v[0] + v[1]) + (v[2] + v[3]), sh);
+    const int64_t nb = (n - (int64_t)blockIdx.x * PB) < PB ? (n - (int64_t)blockIdx.x * PB) : PB;
+    const double mu = s / (double)nb;
+    double a = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < cnt) { const double d = v[k] - mu; a = fma(d, d, a); }
+    a = block_sum_256(a, sh);
+    if (threadIdx.x == 0) { tot[blockIdx.x] = s; dev[blockIdx.x] = a; }
+}
+
+__global__ void __launch_bounds__(256) k_moments_finish(const double* tot, const double* dev, int64_t nblk, int64_t n,
+                                                       double* stat) {
+    __shared__ double sh[9];
+    double a = 0.0;
+    for (int64_t b = threadIdx.x; b < nblk; b += 256) a += tot[b];
+    const double mean = block_sum_256(a, sh) / (double)n;
+    double m2 = 0.0;
+    for (int64_t b = threadIdx.x; b < nblk; b += 256) {
+        const int64_t nb = (n - b * PB) < PB ? (n - b * PB) : PB;
+        const double d = tot[b] / (double)nb - mean;
+        m2 += dev[b] + (double)nb * d * d;
+    }
+    m2 = block_sum_256(m2, sh);
+    if (threadIdx.x == 0) { stat[0] = mean; stat[1] = sqrt(m2 / (double)n); }
+}
+
 __device__ __forceinline__ double range_sum(const double* P, const double* T2, int64_t s, int64_t e) {
     const int64_t bs = s / PB, be = (e - 1) / PB;
     const double head = (s % PB) ? P[s - 1] : 0.0;
@@ -149,10 +191,16 @@ __global__ void __launch_bounds__(256) k_binrms_main(const double* P, const doub
 // point is in).  HBM traffic is one pass over the series (+ halo) instead of 2-4
 // sectors per bin.  acc[i] (shared) collects sum of mean^2 per bin size over
 // the CTA's tiles in a fixed order; partial[cta, i] leaves at the end.
-constexpr int TT = 8192;
+#ifndef MC3B_TT
+#define MC3B_TT 8192
+#endif
+constexpr int TT = MC3B_TT;
 constexpr int BMAX = 4096;
 constexpr int BWARP = 256;
-constexpr int TNW = 16;            // warps per CTA of the tile kernel          // bin sizes below this: one warp per size; above: one lane per size
+#ifndef MC3B_TNW
+#define MC3B_TNW 16
+#endif
+constexpr int TNW = MC3B_TNW;            // warps per CTA of the tile kernel          // bin sizes below this: one warp per size; above: one lane per size
 
 // Skewed shared-memory index: a bin size b makes the lanes of a warp read the
 // prefix with stride b; padding one slot per 16, 256 and 4096 entries spreads
@@ -296,7 +344,15 @@ __global__ void k_binrms_finish(const double* partial, int ys, int64_t n, int64_
     if (i >= nout) return;
     const int64_t b = 1 + i * binstep, M = n / b;
     double a = 0.0;
-    for (int y = 0; y < ys; y++) a += partial[(int64_t)y * nout + i];
+    int y = 0;
+    for (; y + 16 <= ys; y += 16) {                  // 16 loads in flight, added in row order
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) v[k] = partial[(int64_t)(y + k) * nout + i];
+#pragma unroll
+        for (int k = 0; k < 16; k++) a += v[k];
+    }
+    for (; y < ys; y++) a += partial[(int64_t)y * nout + i];
     const double r = sqrt(a / (double)M);
     rms[i] = r;
     rmslo[i] = rmshi[i] = r / sqrt(2.0 * (double)M);
@@ -378,6 +434,20 @@ __global__ void k_fill_int(int* p, int n, int v) {
 }
 
 // ---- binarray ---------------------------------------------------------------
+// 1/sigma^2 without the FP64 division sequence (~30 instructions and a slow path):
+// single-precision reciprocal as a seed, two Newton steps in fp64 (relative error
+// < 2e-16 after the second; the reference's 1/(s*s) is rounded once more, so the
+// two agree to ~3e-16).  Values whose square leaves the float range take the exact
+// division.
+__device__ __forceinline__ double inv_square(double s) {
+    const double v = s * s;
+    if (!(v > 1e-30 && v < 1e30)) return 1.0 / v;
+    double r = (double)__frcp_rn((float)v);
+    r = fma(r, fma(-v, r, 1.0), r);
+    r = fma(r, fma(-v, r, 1.0), r);
+    return r;
+}
+
 template <bool W>
 __global__ void __launch_bounds__(256) k_binarray_big(const double* d, const double* u, int64_t binsize, double* bd,
                                                      double* bs) {
@@ -386,7 +456,7 @@ __global__ void __launch_bounds__(256) k_binarray_big(const double* d, const dou
     double a = 0.0, w = 0.0;
     for (int64_t k = threadIdx.x; k < binsize; k += 256) {
         if (W) {
-            const double s = u[e0 + k], ww = 1.0 / (s * s);
+            const double ww = inv_square(u[e0 + k]);
             w += ww;
             a += d[e0 + k] * ww;
         } else {
@@ -441,7 +511,7 @@ __global__ void __launch_bounds__(256) k_binarray_direct(const double* __restric
                 for (int j = 0; j < 8; j++) {
                     if (W) {
                         const int64_t k = base + lane + 32 * j;
-                        const double ww = (k < binsize) ? 1.0 / (sg[q][j] * sg[q][j]) : 0.0;
+                        const double ww = (k < binsize) ? inv_square(sg[q][j]) : 0.0;
                         w[q] += ww;
                         a[q] = fma(v[q][j], ww, a[q]);
                     } else {
@@ -479,7 +549,7 @@ __global__ void __launch_bounds__(256) k_binarray_short(const double* __restrict
     const double* x = d + b * binsize;
     double a = 0.0, w = 0.0;
     for (int k = 0; k < binsize; k++) {
-        if (W) { const double s0 = u[b * binsize + k], q0 = 1.0 / (s0 * s0); w += q0; a = fma(x[k], q0, a); }
+        if (W) { const double q0 = inv_square(u[b * binsize + k]); w += q0; a = fma(x[k], q0, a); }
         else a += x[k];
     }
     if (W) {
@@ -517,7 +587,11 @@ RmsLayout rms_layout(int64_t n, int64_t maxbins, int64_t binstep, bool allow_til
     int sms = mc3b_sm_count();
     if (sms <= 0) sms = 148;
     const size_t tile_smem = tile_smem_bytes(L.halo, L.nsmall);
-    L.tile_ctas = sms * (tile_smem <= 100 * 1024 ? 2 : 1);
+    int per_sm = (int)((227 * 1024) / (tile_smem + 1024));          // resident CTAs: shared memory ...
+    if (per_sm > 2048 / (TNW * 32)) per_sm = 2048 / (TNW * 32);       // ... and threads
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = getenv("MC3B_TILE_CTAS")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    L.tile_ctas = sms * per_sm;
     const int64_t ntiles = ceil_div64(n, TT);
     if (L.tile_ctas > ntiles) L.tile_ctas = (int)ntiles;
     L.need_prefix = L.nsmall < L.nout;
@@ -558,15 +632,21 @@ extern "C" int mc3b_binrms(const double* data, int64_t n, int64_t maxbins, int64
     double *P = w + L.oP, *tot = w + L.oTot, *T2 = w + L.oT2, *dev = w + L.oDev, *part = w + L.oPart;
     double *ig = w + L.oIg, *lohi = w + L.oLohi, *stat = w + L.oStat;
     int* lead = (int*)(w + L.oLead);
-    if (L.need_prefix) k_block_prefix<true><<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
-    else k_block_prefix<false><<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
-    MC3B_CHECK_LAUNCH("k_block_prefix");
-    k_totals_scan<<<1, 256, 0, st>>>(tot, L.nblk, n, T2, stat);
-    MC3B_CHECK_LAUNCH("k_totals_scan");
-    k_dev2<<<(unsigned)L.nblk, 256, 0, st>>>(data, n, stat, dev);
-    MC3B_CHECK_LAUNCH("k_dev2");
-    k_std<<<1, 256, 0, st>>>(dev, L.nblk, n, stat);
-    MC3B_CHECK_LAUNCH("k_std");
+    if (L.need_prefix) {
+        k_block_prefix<true><<<(unsigned)L.nblk, 256, 0, st>>>(data, n, P, tot);
+        MC3B_CHECK_LAUNCH("k_block_prefix");
+        k_totals_scan<<<1, 256, 0, st>>>(tot, L.nblk, n, T2, stat);
+        MC3B_CHECK_LAUNCH("k_totals_scan");
+        k_dev2<<<(unsigned)L.nblk, 256, 0, st>>>(data, n, stat, dev);
+        MC3B_CHECK_LAUNCH("k_dev2");
+        k_std<<<1, 256, 0, st>>>(dev, L.nblk, n, stat);
+        MC3B_CHECK_LAUNCH("k_std");
+    } else {                                             // mean and std in one streaming pass
+        k_moments<<<(unsigned)L.nblk, 256, 0, st>>>(data, n, tot, dev);
+        MC3B_CHECK_LAUNCH("k_moments");
+        k_moments_finish<<<1, 256, 0, st>>>(tot, dev, L.nblk, n, stat);
+        MC3B_CHECK_LAUNCH("k_moments_finish");
+    }
     MC3B_CUDA(cudaMemsetAsync(part, 0, sizeof(double) * (size_t)L.rows * L.nout, st));
     if (L.nsmall > 0) {
         const size_t smem = tile_smem_bytes(L.halo, L.nsmall);

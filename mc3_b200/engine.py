@@ -344,13 +344,21 @@ class Population:
     # ------------------------------------------------------------------
     # chi-squared of a batch of full parameter vectors
     # ------------------------------------------------------------------
+    def _plan_chains(self, nb):
+        """Chain count the launch shape of an nb-row launch is planned for: nb itself,
+        or -- with plan_chains -- the whole population (`_plan_rows` while a larger
+        batch, the initial-population trials, is evaluated in per-device blocks)."""
+        if not self.plan_chains:
+            return nb
+        return max(self.plan_chains, getattr(self, '_plan_rows', 0), nb)
+
     def _plan(self, nb):
-        if nb not in self._plans:
+        key = self._plan_chains(nb)
+        if key not in self._plans:
             ns = ctypes.c_int(0)
-            _lib.call('mc3b_model_chisq_plan', max(self.plan_chains, nb), self.ndata,
-                      self.dtype, ctypes.byref(ns))
-            self._plans[nb] = ns.value
-        return self._plans[nb]
+            _lib.call('mc3b_model_chisq_plan', key, self.ndata, self.dtype, ctypes.byref(ns))
+            self._plans[key] = ns.value
+        return self._plans[key]
 
     def _workspace(self, key, shape, dtype=torch.float64):
         t = self._work.get(key)
@@ -417,9 +425,9 @@ class Population:
             return out, nb, 1
         if self.kind == 'builtin':
             ns = self._plan(nb)
-            part = self._workspace(('part', nb), (ns, nb))
+            part = self._workspace(('part', nb, ns), (ns, nb))
             o = _lib.ChisqOpts()
-            o.plan_chains = max(self.plan_chains, nb) if self.plan_chains else 0
+            o.plan_chains = self._plan_chains(nb) if self.plan_chains else 0
             o.uniform_sigma = 1 if self.usig else 0
             if fuse is not None:
                 o.c_off, o.gen, o.zrow0, adv = fuse
@@ -515,6 +523,13 @@ class Population:
         rows and the blocks are all-gathered (the trials themselves are Philox
         draws every device generates identically)."""
         nt = trial.shape[0]
+        self._plan_rows = nt          # one launch shape for the batch, however it is split over devices
+        try:
+            return self._trial_log_post_blocks(trial, nt)
+        finally:
+            self._plan_rows = 0
+
+    def _trial_log_post_blocks(self, trial, nt):
         if self.world == 1 or self.shard != 'chains':
             return -0.5*self.chisq(trial)
         per = -(-nt//self.world)

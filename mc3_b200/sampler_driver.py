@@ -269,10 +269,7 @@ def sample(data=None, uncert=None, func=None, params=None,
 
     root = os.path.splitext(savefile)[0] if savefile is not None else 'mc3'
     stats_file = f'{root}_statistics.txt'
-    with open(stats_file, 'w') as f:
-        f.write("# Parameter name     best fit   median      1sigma_low   "
-                "1sigma_hi        S/N\n")
-        f.write('\n'.join(rows) + '\n' + fit_txt)
+    ms.summary_stats(stat_post, output, filename=stats_file)      # stats.py:967-1112
     log.msg('\nFor a detailed summary with all parameter posterior statistics '
             f'see {stats_file}')
     log.msg("\nOutput sampler files:")

@@ -18,7 +18,8 @@ from . import _lib
 
 __all__ = ['bin_array', 'residuals', 'chisq', 'dwt_chisq', 'dwt_daub4',
            'time_avg', 'gelman_rubin', 'log_prior', 'cred_region',
-           'marginal_statistics', 'calc_sample_statistics', 'hpd_statistics']
+           'marginal_statistics', 'calc_sample_statistics', 'hpd_statistics',
+           'summary_stats']
 
 
 def _dev():
@@ -333,3 +334,56 @@ def calc_sample_statistics(posterior, bestp, pstep, quantile=0.683,
                                                  pdf=pdf, xpdf=xpdf)
         res += [expand(mode), expand(hlo), expand(hhi)]
     return tuple(res)
+
+
+def summary_stats(posterior, mc3_output, filename=None, device=True):
+    """The reference's `<root>_statistics.txt` (mc3/stats/stats.py:967-1112): medians,
+    means, best fit and marginal modes, standard deviations, 1/2-sigma central and
+    highest-posterior-density intervals (machine readable, then LaTeX), and the fit
+    statistics.  `posterior` is the burned (and thinned to <= 20000 rows) sample of
+    the free parameters; HPD statistics come from the GPU unless device=False."""
+    import sys
+    from . import utils as mu
+    bestp, pstep = mc3_output['bestp'], np.asarray(mc3_output['pstep'])
+    pnames, texnames = mc3_output['pnames'], mc3_output['texnames']
+    npars = len(bestp)
+    s1 = calc_sample_statistics(posterior, bestp, pstep, 0.683, calc_hpd=True, device=device)
+    s2 = calc_sample_statistics(posterior, bestp, pstep, 0.9545, calc_hpd=True, device=device)
+    median, mean, std, mode = s1[0], s1[1], s1[2], s1[5]
+    cols = '2sigma_low     1sigma_low     1sigma_up      2sigma_up      Parameter'
+    lines = ['Summary of posterior statistics:', '', 'Parameter estimates:',
+             ' Median         Mean           Max-posterior  Mode           Parameter']
+    lines += [f'{median[i]:14.7e} {mean[i]:14.7e} {bestp[i]:14.7e} {mode[i]:14.7e}  {pnames[i]}'
+              for i in range(npars)]
+    lines += ['', ' Std_deviation  Parameter']
+    lines += [f'{std[i]:14.7e}  {pnames[i]}' for i in range(npars)]
+    for title, lo2, lo1, hi1, hi2 in (
+            ('Central quantile credible intervals:', s2[3], s1[3], s1[4], s2[4]),
+            ('Highest-posterior-density credible intervals:', s2[6], s1[6], s1[7], s2[7])):
+        lines += ['', title, ' ' + cols]
+        lines += [f'{lo2[i]:14.7e} {lo1[i]:14.7e} {hi1[i]:14.7e} {hi2[i]:14.7e}  {pnames[i]}'
+                  for i in range(npars)]
+    lines += ['', '', 'LaTeX format']
+    for k, (title, val, lo, hi) in enumerate((
+            ('Median and 1sigma central-quantile statistics', median, s1[3], s1[4]),
+            ('Median and 2sigma central-quantile statistics', median, s2[3], s2[4]),
+            ('Marginal max_posterior (mode) and 1sigma-HPD statistics', mode, s1[6], s1[7]),
+            ('Marginal max_posterior (mode) and 2sigma-HPD statistics', mode, s2[6], s2[7]))):
+        tex = mu.tex_parameters(val, lo, hi, significant_digits=2)
+        lines += ([] if k == 0 else ['']) + [title]
+        lines += [f'{texnames[i]}  &  {tex[i]}' for i in range(npars)]
+    bic = mc3_output['BIC']
+    fmt = len(f'{bic:.4f}')
+    lines += ['', '',
+              f"Best-parameter's chi-squared:       {mc3_output['best_chisq']:{fmt}.4f}",
+              f"Best-parameter's -2*log(posterior): {-2.0*mc3_output['best_log_post']:{fmt}.4f}",
+              f"Bayesian Information Criterion:     {bic:{fmt}.4f}",
+              f"Reduced chi-squared:                {mc3_output['red_chisq']:{fmt}.4f}",
+              f"Standard deviation of residuals:  {mc3_output['stddev_residuals']:.6g}", '', '', '']
+    text = '\n'.join(lines)
+    if filename is None:
+        sys.stdout.write(text)
+    else:
+        with open(filename, 'w') as f:
+            f.write(text)
+    return text

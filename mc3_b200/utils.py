@@ -74,6 +74,32 @@ class Log:
             self.file.close()
 
 
+def tex_parameters(values, low_bounds, high_bounds, names=None, significant_digits=2):
+    """LaTeX strings `value^{+hi}_{-lo}` with the number of decimals that shows
+    `significant_digits` of the smaller error bar (mc3/utils/utils.py:364-468;
+    a missing value prints the interval, a fixed parameter just the value)."""
+    from decimal import Decimal
+    out = []
+    for k, value in enumerate(values):
+        if value is None or np.isnan(value):
+            lo, hi = low_bounds[k], high_bounds[k]
+            place = Decimal(lo - hi).adjusted()
+            dec = int(np.clip(significant_digits - 1 - place, 1, 10))
+            text = f'[{lo:.{dec}f}, {hi:.{dec}f}]'
+        else:
+            lo, hi = low_bounds[k] - value, high_bounds[k] - value
+            place = min(Decimal(lo).adjusted(), Decimal(hi).adjusted())
+            dec = int(np.clip(significant_digits - 1 - place, 1, 10))
+            text = f'{value}' if lo == hi else \
+                f'{value:>.{dec}f}^{{{hi:+.{dec}f}}}_{{{lo:+.{dec}f}}}'
+        prefix = '$'
+        if names is not None:                       # names may carry their own math mode
+            name = names[k].strip()
+            prefix = f'{name[:-1]} = ' if name.startswith('$') and name.endswith('$') else f'{name}$ = '
+        out.append(f'{prefix}{text}$')
+    return out
+
+
 def default_parnames(npars):
     return np.array([f'Param {i+1}' for i in range(npars)])
 

@@ -168,6 +168,44 @@ def hpd_golden(R):
             g[f'{name}_{q}'] = v
     np.savez(os.path.join(GOLD, 'hpd.npz'), **g)
     print('hpd.npz:', len(g), 'entries')
+    # the reference's <root>_statistics.txt for the same sample (stats.py:967-1112);
+    # `post` only needs the attributes summary_stats reads
+    import types
+    ifree = np.where(pstep > 0)[0]
+    pdfs = [R.stats.cred_region(post[:, i])[0:2] for i in range(post.shape[1])]
+    fake = types.SimpleNamespace(posterior=post, bestp=bestp[ifree], npars=post.shape[1],
+                                 pnames=[f'p{i}' for i in range(post.shape[1])],
+                                 pdf=[p[0] for p in pdfs], xpdf=[p[1] for p in pdfs])
+    out = {'bestp': bestp, 'pstep': pstep, 'pnames': [f'Param {i+1}' for i in range(len(bestp))],
+           'texnames': [rf'$\\alpha_{i}$' for i in range(len(bestp))], 'best_chisq': 1234.56789,
+           'best_log_post': -620.0, 'BIC': 1290.123456, 'red_chisq': 1.0345678,
+           'stddev_residuals': 0.4987654321}
+    R.stats.summary_stats(fake, out, filename=os.path.join(GOLD, 'summary_stats.txt'))
+    print('summary_stats.txt written')
+
+
+def savefile_golden(R):
+    """A savefile as the REFERENCE writes it (mcmc_driver.py:321-324 / np.savez of the
+    output dict): the wire format resume=True must read."""
+    import tempfile
+    p = pb.mcmc_case('sine')
+    func = om.MODELS[p['model']]
+    random.randint = lambda a, b: pb.CHILD_SEED
+    np.random.seed(pb.PARENT_SEED)
+    log = R.utils.Log(verb=0)
+    with tempfile.TemporaryDirectory() as d:
+        sv = os.path.join(d, 'ref_run.npz')
+        out = R.mcmc_driver.mcmc(
+            p['data'], np.copy(p['uncert']), func, np.copy(p['params']), [p['x']], {},
+            p['pmin'], p['pmax'], p['pstep'], p['prior'], p['priorlow'], p['priorup'],
+            p['nchains'], 1, p['nsamples'], 'demc', False, None, True, 0.0, 0.5,
+            p['burnin'], p['thinning'], 1.0, p['fepsilon'], 10, 'normal', sv, False, log,
+            None, None)
+        out['chisq_factor'] = 1.0                  # sampler_driver.py:563-565 adds it before the final save
+        np.savez(sv, **out)
+        with open(sv, 'rb') as f, open(os.path.join(GOLD, 'ref_savefile_sine_demc.npz'), 'wb') as g:
+            g.write(f.read())
+    print('ref_savefile_sine_demc.npz: keys', sorted(out.keys()))
 
 
 def main():
@@ -179,9 +217,13 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'hpd':
         hpd_golden(R)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'savefile':
+        savefile_golden(R)
+        return
     kernels_golden(R)
     mcmc_golden(R)
     hpd_golden(R)
+    savefile_golden(R)
 
 
 if __name__ == '__main__':

@@ -286,3 +286,47 @@ def test_hpd_statistics_on_device_match_reference_golden(mc3):
         sel = xpdf[pdf > hmin]
         np.testing.assert_allclose([mode[i], lo[i], hi[i]], [xpdf[np.argmax(pdf)], sel.min(), sel.max()],
                                    rtol=1e-6, atol=1e-9)
+
+
+def test_resume_from_reference_written_savefile_and_gelman_rubin(mc3, tmp_path):
+    """resume=True reads a savefile written by the REFERENCE (tests/golden/
+    ref_savefile_sine_demc.npz: np.savez of its output dict, mcmc_driver.py:321-324):
+    the old samples come first, every chain restarts from its last row
+    (chain.py:166-169), and Gelman-Rubin counts each chain's earlier samples
+    (burn-in from the start of the chain, gelman.py:43-55)."""
+    import os
+    import shutil
+    from mc3_b200.mcmc_driver import mcmc
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'ref_savefile_sine_demc.npz')
+    sv = str(tmp_path/'run.npz')
+    shutil.copy(gold, sv)
+    old = np.load(gold)
+    p = pb.mcmc_case('sine')
+    out = mcmc(p['data'], p['uncert'], mc3.models.sinusoid, p['params'], [p['x']], {},
+               p['pmin'], p['pmax'], p['pstep'], p['prior'], p['priorlow'], p['priorup'],
+               8, None, 1600, 'demc', False, None, True, 0.0, 0.5, 40, 2, 1.0, 0.01,
+               10, 'normal', sv, True, mc3.Log(verb=-1), None, None, seed=5,
+               return_population=True)
+    pop = out.pop('_population')
+    n_old = old['posterior'].shape[0]
+    assert out['posterior'].shape[0] == n_old + 800
+    assert np.array_equal(out['posterior'][:n_old], old['posterior'])
+    assert np.array_equal(out['zchain'][:n_old], old['zchain'])
+    assert np.array_equal(out['log_post'][:n_old], old['log_post'])
+    assert np.array_equal(out['zchain'][n_old:], np.tile(np.arange(8), 100))
+    # first new row of chain c follows its last old state
+    for c in range(8):
+        last = old['posterior'][np.where(old['zchain'] == c)[0][-1]]
+        first_new = out['posterior'][n_old + c]
+        assert np.all(np.abs(first_new - last) < 30*p['pstep'])
+    # Gelman-Rubin over old + new samples, burn-in taken from the start of each chain
+    got = pop.gelman_rubin(20)
+    want = ok.gelman_rubin(out['posterior'], out['zchain'], 20)
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    # the file was rewritten with the reference's key set and loads again
+    with np.load(sv) as f:
+        assert f['posterior'].shape[0] == n_old + 800
+        for k in ('posterior', 'zchain', 'chisq', 'log_post', 'acceptance_rate', 'bestp',
+                  'best_chisq', 'red_chisq', 'BIC', 'best_log_post', 'best_model',
+                  'stddev_residuals', 'burnin', 'pstep', 'ifree'):
+            assert k in f.files, k

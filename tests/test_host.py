@@ -160,3 +160,23 @@ def test_sample_statistics_host_path_matches_reference_golden():
         st = ms.calc_sample_statistics(post, bestp, pstep, quantile=q, calc_hpd=True)
         for name, v in zip(('median', 'mean', 'std', 'med_lo', 'med_hi', 'mode', 'hpd_lo', 'hpd_hi'), st):
             np.testing.assert_allclose(v, g[f'{name}_{q}'], rtol=1e-9, atol=1e-12, err_msg=name)
+
+
+def test_summary_stats_text_matches_reference_golden(tmp_path):
+    """<root>_statistics.txt: same text as the reference's summary_stats
+    (stats.py:967-1112) on the seeded sample of problems.hpd_case
+    (tests/golden/summary_stats.txt, written by oracle/make_golden.py)."""
+    import os
+    import numpy as np
+    from mc3_b200 import stats as ms
+    from oracle import problems as pb
+    here = os.path.dirname(os.path.abspath(__file__))
+    want = open(os.path.join(here, 'golden', 'summary_stats.txt')).read()
+    post, bestp, pstep = pb.hpd_case()
+    out = {'bestp': bestp, 'pstep': pstep, 'pnames': [f'Param {i+1}' for i in range(len(bestp))],
+           'texnames': [rf'$\\alpha_{i}$' for i in range(len(bestp))], 'best_chisq': 1234.56789,
+           'best_log_post': -620.0, 'BIC': 1290.123456, 'red_chisq': 1.0345678,
+           'stddev_residuals': 0.4987654321}
+    got = ms.summary_stats(post, out, filename=str(tmp_path/'s.txt'), device=False)
+    assert got == open(tmp_path/'s.txt').read()
+    assert got == want
