@@ -34,6 +34,7 @@ template <class M, typename T, int LC, int CPT, bool USIG>
 __global__ void __launch_bounds__(WARPS * 32, (CPT == 2 ? MC3B_RESIDENT2 : RESIDENT)) k_model_chisq(ChisqArgs<T> a) {
     constexpr int TILE = tilecfg<T>::TILE;
     constexpr int LP = 32 / LC;
+    asm volatile("griddepcontrol.launch_dependents;");   // the next proposal kernel may start its draws
     __shared__ __align__(128) T sx[STAGES][TILE];
     __shared__ __align__(128) T sd[STAGES][TILE];
     __shared__ __align__(128) T sw[STAGES][TILE];

@@ -74,18 +74,34 @@ static __device__ __noinline__ void fused_metropolis_tail(const mc3b_sampler_t* 
 // chains_per_cta: chains a CTA covers (its thread t < chains_per_cta owns chain
 // blockIdx.x * chains_per_cta + t of the launch).  `f` must be the kernel
 // parameter itself (read from the constant bank, never copied to the stack).
+//
+// The reducer of a chain group is the CTA of its LAST split: CTAs are dispatched in
+// block order, so it starts after every other split of the group is running or done,
+// and with the decreasing split schedule it is also the shortest.  The other CTAs
+// publish their row with one fire-and-forget reduction (no round trip: an atomic
+// whose result every CTA waited for cost ~10 us per launch over the six waves) and
+// leave; the reducer spins until all nsplit-1 arrivals are in.
 __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double* partial, int64_t ldpartial,
                                                  int64_t nchains, int chains_per_cta) {
-    __shared__ int s_last;
     __shared__ __align__(16) mc3b_sampler_t sS;
-    __threadfence();                               // this CTA's partial row before its arrival
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&f.done[blockIdx.x], 1) == (int)gridDim.y - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
     __shared__ double vbuf[STAGE_DOUBLES];
-    if (threadIdx.x == 0) sS = f.S;                // constant bank -> shared, static offsets only
+    __syncthreads();                               // the CTA's partial row is written
+    const int others = (int)gridDim.y - 1;
+    if ((int)blockIdx.y != others) {
+        if (threadIdx.x == 0) {
+            __threadfence();                       // cumulative over the barrier: the row before the count
+            atomicAdd(&f.done[blockIdx.x], 1);
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        sS = f.S;                                  // constant bank -> shared, static offsets only
+        int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(f.done + blockIdx.x) : "memory");
+        } while (seen < others);
+        f.done[blockIdx.x] = 0;                    // every arrival is in: ready for the next launch
+    }
     __syncthreads();
     if (threadIdx.x < 32) {                        // one warp stages the per-parameter vectors
         mc3b_sampler_t T = sS;
@@ -109,17 +125,14 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
     if ((int)threadIdx.x < chains_per_cta && cl < nchains)
         fused_metropolis_tail(&sS, partial, ldpartial, (int)gridDim.y, cl, f.c_off, f.gen, f.zrow0);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        f.done[blockIdx.x] = 0;
-        if (f.advance) {
+    if (threadIdx.x == 0 && f.advance) {
+        __threadfence();
+        if (atomicAdd(&f.done[gridDim.x], 1) == (int)gridDim.x - 1) {
+            f.done[gridDim.x] = 0;
             __threadfence();
-            if (atomicAdd(&f.done[gridDim.x], 1) == (int)gridDim.x - 1) {
-                f.done[gridDim.x] = 0;
-                __threadfence();
-                const int64_t g = *sS.gen_dev + 1;
-                *sS.gen_dev = g;
-                if (sS.F_peers) flags_publish(sS, g);    // every group's peer stores are performed
-            }
+            const int64_t g = *sS.gen_dev + 1;
+            *sS.gen_dev = g;
+            if (sS.F_peers) flags_publish(sS, g);    // every group's peer stores are performed
         }
     }
 }

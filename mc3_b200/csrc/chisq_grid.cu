@@ -51,6 +51,7 @@ constexpr int REANCHOR = 4;         // restarts between direct sincos evaluation
 template <bool USIG>
 __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqArgs<double> a) {
     using namespace grid;
+    asm volatile("griddepcontrol.launch_dependents;");   // the next proposal kernel may start its draws
     __shared__ __align__(128) double sd[NSTAGE][TILE];
     __shared__ __align__(128) double sw[USIG ? 1 : NSTAGE][USIG ? 2 : TILE];
     __shared__ __align__(128) double pw[USIG ? 1 : WARPS][USIG ? 2 : TILE];      // per-warp d/sigma

@@ -277,12 +277,12 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg_model(RegArgs a) {
         }
     };
     if (b_begin < b_end) fill(b_begin, 0);
-    for (int64_t b = b_begin; b < b_end; b++) {
-        const int buf = (int)((b - b_begin) & 1);
-        __syncthreads();                             // tile b is complete; tile b-1 is no longer read
-        if (b + 1 < b_end) fill(b + 1, buf ^ 1);
+    // One block; INTERIOR (compile time): every output the block owns exists, so the
+    // squares are summed without a per-element select (the ALU pipe was as busy as the
+    // FP64 pipe: profiles/r2_dwt_reg_model.md).
+    auto do_block = [&](int64_t b, int buf, auto interior_tag) {
+        constexpr bool interior = decltype(interior_tag)::value;
         const int64_t g0 = b * RADV;
-        const bool interior = g0 + RB <= a.n_in;
         double v[18];
         const double2* px = reinterpret_cast<const double2*>(&sxd[buf][0][lane * RPAD]);
         const double2* pd = reinterpret_cast<const double2*>(&sxd[buf][1][lane * RPAD]);
@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg_model(RegArgs a) {
                     const double a0 = v[2 * j], a1 = v[2 * j + 1], a2 = v[2 * j + 2], a3 = v[2 * j + 3];
                     const double sm = fma(c3, a3, fma(c2, a2, fma(c1, a1, c0 * a0)));
                     const double d = fma(-c0, a3, fma(c1, a2, fma(-c2, a1, c3 * a0)));
-                    s2 = fma(d, (interior || lev_pos0 + j < lev_n) ? d : 0.0, s2);
+                    if (interior) s2 = fma(d, d, s2);
+                    else s2 = fma(d, (lev_pos0 + j < lev_n) ? d : 0.0, s2);
                     v[j] = sm;
                 }
             }
@@ -315,7 +316,14 @@ __global__ void __launch_bounds__(CH * 32) k_dwt_reg_model(RegArgs a) {
             cnt = half;
         }
         const int64_t o = (g0 >> 4) + lane;
-        if (live && lane < 30 && o < (a.n_in >> 4)) a.out[c * a.ldo + o] = v[0];
+        if (live && lane < 30 && (interior || o < (a.n_in >> 4))) a.out[c * a.ldo + o] = v[0];
+    };
+    for (int64_t b = b_begin; b < b_end; b++) {
+        const int buf = (int)((b - b_begin) & 1);
+        __syncthreads();                             // tile b is complete; tile b-1 is no longer read
+        if (b + 1 < b_end) fill(b + 1, buf ^ 1);
+        if (b * RADV + RB <= a.n_in) do_block(b, buf, std::true_type{});
+        else do_block(b, buf, std::false_type{});
     }
 #pragma unroll
     for (int l = 0; l < 4; l++) {

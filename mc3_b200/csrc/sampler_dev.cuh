@@ -59,16 +59,14 @@ __device__ __forceinline__ void stage_vectors(mc3b_sampler_t& S, double* buf) {
     S.ifree = ifr;
 }
 
-// Proposal of chain c for generation gen (chain.py:185-247, 251-255).
+// The random numbers chain c consumes in generation gen (chain.py:185, 197-203,
+// 223-229, 257): a function of (seed, chain, generation) only -- not of the chains'
+// states, so a proposal kernel launched as a programmatic dependent of the previous
+// generation's model kernel draws them while that kernel is still running.
 template <bool REPLAY>
-__device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,
-                                              int64_t zsize, int64_t c) {
-    const int nfree = S.nfree, npars = S.npars;
-    // population as of the start of this generation (peer mode: half gen & 1)
-    const double* Xg = S.X_peers ? S.X_peers[S.rank] + (gen & 1) * S.nchains * nfree : S.X;
-    const double* x = Xg + c * nfree;
-    double jump[MAXP], nrm[MAXP];
-    Draws dr;
+__device__ __forceinline__ void chain_draws(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,
+                                            int64_t zsize, int64_t c, Draws& dr, double* nrm) {
+    const int nfree = S.nfree;
     dr.iz = -1; dr.usj = 1.0; dr.gs = 0.0;
 
     if (REPLAY) {
@@ -107,6 +105,17 @@ __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3
             if (j + 1 < nfree) nrm[j + 1] = n1 * S.pstep[S.ifree[j + 1]];
         }
     }
+}
+
+// Jump, bounds, shared parameters and the snooker factor from the draws and the
+// population as of the start of generation gen (chain.py:195-255).
+__device__ __forceinline__ void propose_apply(const mc3b_sampler_t& S, const Draws& dr, const double* nrm,
+                                              int64_t gen, int64_t c) {
+    const int nfree = S.nfree, npars = S.npars;
+    // population as of the start of this generation (peer mode: half gen & 1)
+    const double* Xg = S.X_peers ? S.X_peers[S.rank] + (gen & 1) * S.nchains * nfree : S.X;
+    const double* x = Xg + c * nfree;
+    double jump[MAXP];
 
     double mrfactor = 1.0;
     bool sjump = false;
@@ -177,6 +186,16 @@ __device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3
     S.mrfactor[c] = mrfactor;
     S.u[c] = dr.u;
     S.inb[c] = inb;
+}
+
+// Proposal of chain c for generation gen (chain.py:185-247, 251-255).
+template <bool REPLAY>
+__device__ __forceinline__ void propose_chain(const mc3b_sampler_t& S, const mc3b_draws_t& D, int64_t gen,
+                                              int64_t zsize, int64_t c) {
+    Draws dr;
+    double nrm[MAXP];
+    chain_draws<REPLAY>(S, D, gen, zsize, c, dr, nrm);
+    propose_apply(S, dr, nrm, gen, c);
 }
 
 // Data chi-squared of a proposal: the partial rows of the model kernel added in

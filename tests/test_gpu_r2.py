@@ -330,3 +330,31 @@ def test_resume_from_reference_written_savefile_and_gelman_rubin(mc3, tmp_path):
                   'best_chisq', 'red_chisq', 'BIC', 'best_log_post', 'best_model',
                   'stddev_residuals', 'burnin', 'pstep', 'ifree'):
             assert k in f.files, k
+
+
+def test_dwt_chisq_population_at_config3_size(mc3):
+    """Wavelet likelihood at BASELINE config 3's data size (N = 2^20, white + red noise
+    synthesised by the inverse D4 transform) for a population of 1024 chains: every
+    chain against the oracle's restatement of _dwt.c:56-119 at 1e-10, and identical
+    chains give identical bits."""
+    from mc3_b200 import _lib, workloads
+    w = workloads.config3()
+    n, nb = w['x'].size, 1024
+    rs = np.random.RandomState(8)
+    P = np.tile(w['params'], (nb, 1))
+    P[:, :4] += rs.normal(0, 1, (nb, 4))*np.array([1e-3, 1e-2, 1e-2, 1e-4])
+    P[:, 5:] *= rs.uniform(0.5, 2.0, (nb, 2))
+    P[777] = P[3]
+    dev = torch.device('cuda')
+    dP, dx, dd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (P, w['x'], w['data']))
+    lib = _lib.load()
+    ws = torch.empty(max(lib.mc3b_dwt_workspace(nb, n), 8)//8, dtype=torch.float64, device=dev)
+    out = torch.empty(nb, dtype=torch.float64, device=dev)
+    _lib.call('mc3b_dwt_chisq', mc3.models.box.model_id, dP.data_ptr(), 7, nb, 7, 4,
+              dx.data_ptr(), None, 0, dd.data_ptr(), n, ws.data_ptr(), out.data_ptr(),
+              _lib.stream_ptr())
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert got[777] == got[3]
+    want = np.array([ok.dwt_chisq(om.box(p[:4], w['x']), w['data'], p) for p in P])
+    np.testing.assert_allclose(got, want, rtol=R64)
