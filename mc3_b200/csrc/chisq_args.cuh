@@ -126,7 +126,9 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
         fused_metropolis_tail(&sS, partial, ldpartial, (int)gridDim.y, cl, f.c_off, f.gen, f.zrow0);
     __syncthreads();
     if (threadIdx.x == 0 && f.advance) {
-        __threadfence();
+        // one fence for the CTA's stores (cumulative over the barrier): system scope when they
+        // went to peer devices, so that the flag below needs no fence of its own
+        if (sS.X_peers) __threadfence_system(); else __threadfence();
         if (atomicAdd(&f.done[gridDim.x], 1) == (int)gridDim.x - 1) {
             f.done[gridDim.x] = 0;
             __threadfence();

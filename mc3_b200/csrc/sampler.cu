@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(128) k_metropolis(mc3b_sampler_t S, const doub
     }
     const double nxt = S.inb[c] ? sum_partials<false>(partial, ldpartial, nsplit, c - c_off) : 0.0;
     metropolis_chain(S, nxt, gen, zrow0, c);
+    if (S.X_peers) __threadfence_system();           // peer stores performed before the kernel ends (k_advance publishes)
 }
 
 __global__ void __launch_bounds__(128) k_init_trials(mc3b_sampler_t S, int kickoff, int64_t ntrials, int64_t round,

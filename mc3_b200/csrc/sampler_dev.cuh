@@ -21,8 +21,9 @@ __device__ __forceinline__ void box_muller(double u1, double u2, double& n0, dou
 }
 
 // Peer-memory exchange: generation flags (include/mc3b200.h, F_peers).
+// Precondition: every CTA that stored into peers has executed a system fence (after a CTA
+// barrier) before the event that let this thread know the generation is complete.
 __device__ __forceinline__ void flags_publish(const mc3b_sampler_t& S, int64_t done) {
-    __threadfence_system();                          // this device's peer stores first
     for (int p = 0; p < S.world; p++)
         asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(S.F_peers[p] + S.rank), "l"((long long)done)
                      : "memory");
@@ -281,7 +282,8 @@ __device__ __forceinline__ void metropolis_chain(const mc3b_sampler_t& S, double
                 else S.Z[row * nfree + j] = v;
             }
         }
-        __threadfence_system();
+        // (no fence here: the caller orders the CTA's peer stores with ONE system fence after
+        // a CTA barrier, before it counts the group as done -- see fused_metropolis / k_metropolis)
     }
     if (write) {
         S.log_post[row] = -0.5 * cur;
