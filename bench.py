@@ -351,8 +351,15 @@ def run_ours(args):
         # each occupies the pipe like one FMA (2 flops) -- or 1.5x that when it reads
         # three fresh registers (profiles/r1_fp64_peak_probe.txt), which the peak
         # probe's FMAs never do, so fp64_pipe_frac understates the pipe's busy time.
-        pipe_instr = 6.0 if getattr(pop, 'grid', False) else (19.0 if pop.usig else 20.0)
-        kname = ('k_sinegrid<USIG=%s>' % ('true' if pop.usig else 'false')) \
+        # The mirrored-pair kernel (k_sinefold) needs 425 per 128-point tile = 3.32: two points
+        # share one sine/cosine product pair, so `frac` (SURVEY's 10 algorithmic flops per
+        # chain-point over the FMA peak) can exceed what a per-point evaluation could reach;
+        # fp64_pipe_frac is the executed-instruction view of the same launch.
+        folded = getattr(pop, 'd_fold', None) is not None
+        pipe_instr = (425.0/128.0 if folded else 6.0) if getattr(pop, 'grid', False) \
+            else (19.0 if pop.usig else 20.0)
+        kname = ('k_sinefold' if folded else
+                 'k_sinegrid<USIG=%s>' % ('true' if pop.usig else 'false')) \
             if getattr(pop, 'grid', False) else 'k_model_chisq<SineModel>'
         roof = {'bound': 'fp64' if args.dtype == 'f64' else 'fp32',
                 'kernel': kname,

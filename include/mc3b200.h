@@ -101,7 +101,16 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
  *                c_off, c_off + nchains) would -- without the second launch.  fuse_done:
  *                device int32[groups + 1] (groups <= nchains/32 + 1), zero before the
  *                first use, left zero by every launch.  advance: the last group also
- *                increments *fuse->gen_dev (replaces mc3b_advance). */
+ *                increments *fuse->gen_dev (replaces mc3b_advance).
+ * folded         non-NULL (fp64, MC3B_MODEL_SINUSOID_GRID, uniform_sigma): the copy of
+ *                `data` written by mc3b_fold_data; the kernel then works on point pairs
+ *                mirrored about block centres (3.3 instead of 6 FP64 instructions per
+ *                chain and point, same rounding-error class; csrc/chisq_grid.cu).
+ * work           with `folded`: device workspace of MC3B_FOLD_WORK * nchains doubles; the
+ *                per-chain constants of the kernel (wavenumber, the sine/cosine tables of
+ *                the pair offsets, block and restart rotations) are then derived once per
+ *                chain by a small kernel launched first, instead of by each of the nsplit
+ *                CTAs of a chain group.  NULL: every CTA derives them (same bits). */
 struct mc3b_sampler;
 typedef struct mc3b_chisq_opts {
     int64_t plan_chains;
@@ -110,7 +119,18 @@ typedef struct mc3b_chisq_opts {
     const struct mc3b_sampler* fuse;
     int32_t* fuse_done;
     int64_t c_off, gen, zrow0;
+    const void* folded;
+    void* work;
 } mc3b_chisq_opts_t;
+#define MC3B_FOLD_WORK 21
+
+/* Chain-independent preparation for `folded` above: per block of 16 points, pair
+ * p = 0..7 joins points 7-p and 8+p of the block;
+ *   out[16 b + 2 p] = -(d_hi + d_lo)/2,   out[16 b + 2 p + 1] = -(d_hi - d_lo)/2.
+ * data, out: [n] fp64 device arrays (the n % 16 trailing entries of out are left
+ * untouched).  Done once per data set.  (No reference counterpart: the reference
+ * evaluates one residual per point, _chisq.c:111-140.) */
+int mc3b_fold_data(const double* data, int64_t n, double* out, void* stream);
 
 int mc3b_model_chisq_ex(int model_id, int dtype, const double* params, int64_t ldp,
                         int64_t nchains, int nmodel, const void* x,

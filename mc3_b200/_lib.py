@@ -46,7 +46,10 @@ class ChisqOpts(ctypes.Structure):
     """mc3b_chisq_opts_t."""
     _fields_ = [('plan_chains', c_i64), ('uniform_sigma', c_i32), ('advance', c_i32),
                 ('fuse', ctypes.POINTER(SamplerStruct)), ('fuse_done', c_vp),
-                ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64)]
+                ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64), ('folded', c_vp), ('work', c_vp)]
+
+
+FOLD_WORK = 21                    # MC3B_FOLD_WORK
 
 
 class DrawsStruct(ctypes.Structure):
@@ -68,6 +71,7 @@ _SIGS = {
     'mc3b_model_chisq_ex': (c_int, [c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp,
                                     c_vp, c_vp, c_i64, c_vp, c_i64, c_int,
                                     ctypes.POINTER(ChisqOpts), c_vp]),
+    'mc3b_fold_data': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),
     'mc3b_chisq_finish': (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,

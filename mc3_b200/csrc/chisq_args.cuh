@@ -50,6 +50,10 @@ template <typename T> struct ChisqArgs {
     const double* params;
     int64_t ldp, nchains;
     const T *x, *d, *w;
+    const T* fold;                  // mirrored-pair copy of d (mc3b_fold_data) or nullptr
+    const double* consts;           // k_sinefold: per-chain constants [NCONST, ldc] (k_fold_consts) or nullptr
+    int64_t ldc;
+    int consts_wait;                // launched as a programmatic dependent of k_fold_consts
     int64_t n;
     double* partial;
     int64_t ldpartial;
@@ -144,3 +148,5 @@ using namespace mc3b_chisq;
 
 // chisq_grid.cu
 int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st);
+int mc3b_launch_sinefold(const ChisqArgs<double>& a, double* work, unsigned groups, unsigned nsplit, cudaStream_t st);
+int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st);

@@ -220,7 +220,255 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
 #endif
 }
 
+// ---- the same model on point PAIRS mirrored about block centres ----------------
+// One uncertainty for all points.  In a block of 16 points with centre phase th_c
+// (between points 7 and 8) the pair p = 0..7 sits at offsets -+dl, dl = p + 1/2:
+//   A sin(th_c +- dl h) = Sc cos(dl h) +- Cc sin(dl h)      (Sc, Cc = A sin/cos th_c)
+//   line(x_c +- dl dx)  = L_c +- sl dx dl
+// so with e = (d+ + d-)/2 and o = (d+ - d-)/2, both chain-independent and prepared
+// ONCE per data set by mc3b_fold_data (stored negated),
+//   u = Sc cp[p] + (L_c - e)          = (r+ + r-)/2
+//   v = Cc sp[p] + (sl dx dl - o)     = (r+ - r-)/2
+//   r+^2 + r-^2 = 2 (u^2 + v^2).
+// Six FP64 instructions per PAIR (t = L_c + ne; u = fma; q = fma(u,u,q); t' = fma(gs,
+// dl, no), dl an immediate; v = fma; q = fma(v,v,q)) plus five per block (rotation of
+// (Sc, Cc) by 16 h, block line): 3.3 per chain-point instead of 6, every one of them
+// with at most two fresh register operands, and the same rounding-error class as the
+// per-point evaluation (no subtraction of large sums: profiles/fold_error.py).  The
+// tables cp/sp[p] = cos/sin((p + 1/2) h) live in 32 registers per chain.  Anchors as in
+// k_sinegrid: (Sc, Cc) restart every RESTART tiles from a rotation of the previous
+// anchor, every REANCHOR-th from fast_sincos_core; 32 block rotations in between.
+// Rotations are stable for any step, so only huge arguments take the direct path.
+// Per-chain constants of the kernel: every CTA of a chain group (105 data splits at
+// config 2) would derive the same 21 numbers through a division and four dependent
+// sine/cosine evaluations before it can touch its first tile (ncu, round 2: a third of
+// all warp time).  k_fold_consts derives them once per chain and launch; the CTAs
+// then start with one round of coalesced loads.  Same formulas, same bits.
+namespace fold {
+constexpr int BLK = 16, NP = BLK / 2;
+constexpr int NCONST = 2 * NP + 5;      // k, cp[NP], sp[NP], c16, s16, cdT, sdT
+struct Consts { double k, cp[NP], sp[NP], c16, s16, cdT, sdT; };
+__device__ __forceinline__ void derive(double period, double dx, Consts& K) {
+    using namespace grid;
+    K.k = 6.283185307179586476925287 / period;
+    const double dth = K.k * dx;
+    double s1, c1;
+    fast_sincos_core(0.5 * dth, K.sp[0], K.cp[0]);
+    fast_sincos_core(dth, s1, c1);
+#pragma unroll
+    for (int i = 1; i < NP; i++) {
+        K.cp[i] = fma(-K.sp[i - 1], s1, K.cp[i - 1] * c1);
+        K.sp[i] = fma(K.cp[i - 1], s1, K.sp[i - 1] * c1);
+    }
+    fast_sincos_core((double)BLK * dth, K.s16, K.c16);
+    fast_sincos_core((double)(RESTART * TILE) * dth, K.sdT, K.cdT);
+}
+}  // namespace fold
+
+__global__ void __launch_bounds__(128) k_fold_consts(const double* __restrict__ params, int64_t ldp, int64_t nchains,
+                                                     const double* __restrict__ x, int64_t n, double* __restrict__ out,
+                                                     int64_t ld) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchains) return;
+    const double x0 = x[0];
+    const double dx = (x[n - 1] - x0) / (double)(n - 1);
+    fold::Consts K;
+    fold::derive(params[c * ldp + 1], dx, K);
+    double* o = out + c;
+    o[0] = K.k;
+#pragma unroll
+    for (int i = 0; i < fold::NP; i++) { o[(1 + i) * ld] = K.cp[i]; o[(1 + fold::NP + i) * ld] = K.sp[i]; }
+    o[(1 + 2 * fold::NP) * ld] = K.c16; o[(2 + 2 * fold::NP) * ld] = K.s16;
+    o[(3 + 2 * fold::NP) * ld] = K.cdT; o[(4 + 2 * fold::NP) * ld] = K.sdT;
+}
+
+#ifndef MC3B_FOLD_MINB
+#define MC3B_FOLD_MINB 4
+#endif
+template <bool PRE>
+__global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqArgs<double> a) {
+    using namespace grid;
+    using fold::BLK; using fold::NP;
+    asm volatile("griddepcontrol.launch_dependents;");
+    __shared__ __align__(128) double sf[NSTAGE][TILE];
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t c = ((int64_t)blockIdx.x * WARPS + warp) * 32 + lane;
+    const bool live = c < a.nchains;
+    if (!live) c = a.nchains - 1;
+
+    const int64_t nfull = a.n / TILE;
+    int64_t tb, te;
+    if (a.nsched > 0) { tb = a.tstart[blockIdx.y]; te = a.tstart[blockIdx.y + 1]; }
+    else { tb = nfull * blockIdx.y / gridDim.y; te = nfull * (blockIdx.y + 1) / gridDim.y; }
+    const int64_t nt = te - tb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t t, int s) {
+        mbar_expect_tx(&full[s], TILE * sizeof(double));
+        bulk_g2s(sf[s], a.fold + t * TILE, TILE * sizeof(double), &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < NSTAGE && s < nt; s++) issue(tb + s, s);
+
+    const double x0 = a.x[0];
+    const double dx = (a.x[a.n - 1] - x0) / (double)(a.n - 1);
+    const double* p = a.params + c * a.ldp;
+    const double amp = p[0], ph = p[2], c0 = p[3], sl = p[4];
+    fold::Consts K;
+    if constexpr (PRE) {
+        if (a.consts_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // k_fold_consts has completed
+        const double* kc = a.consts + c;
+        K.k = kc[0];
+#pragma unroll
+        for (int i = 0; i < NP; i++) { K.cp[i] = kc[(1 + i) * a.ldc]; K.sp[i] = kc[(1 + NP + i) * a.ldc]; }
+        K.c16 = kc[(1 + 2 * NP) * a.ldc]; K.s16 = kc[(2 + 2 * NP) * a.ldc];
+        K.cdT = kc[(3 + 2 * NP) * a.ldc]; K.sdT = kc[(4 + 2 * NP) * a.ldc];
+    } else {
+        fold::derive(p[1], dx, K);
+    }
+    const double k = K.k, c16 = K.c16, s16 = K.s16, cdT = K.cdT, sdT = K.sdT;
+    const double (&cp)[NP] = K.cp;
+    const double (&sp)[NP] = K.sp;
+    const double dth = k * dx;
+    double gs = sl * dx;
+    double dL16 = (double)BLK * gs;
+    asm volatile("" : "+d"(gs), "+d"(dL16));
+    const int keybase = sin_arg_key((double)(RESTART * TILE) * dth) >= MC3B_SIN_KEY_LIMIT ? MC3B_SIN_KEY_LIMIT : 0;
+    auto direct = [&](double x) { return fma(amp, sin(fma(x, k, ph)), fma(sl, x, c0)); };
+
+    double acc = 0.0, S0 = 0.0, C0 = 0.0, Sc = 0.0, Cc = 0.0;
+    int rcount = 0, key = 0;
+    for (int64_t it = 0; it < nt; it++) {
+        const int st = (int)(it % NSTAGE);
+        const uint32_t par = (uint32_t)((it / NSTAGE) & 1);
+        const int tr = (int)(it % RESTART);
+        // centre of the tile's first block: x0 + (first point + 7.5) dx, one rounding
+        const double xc = fma((double)((tb + it) * TILE) + 7.5, dx, x0);
+        if (tr == 0) {
+            const double th = fma(xc, k, ph);
+            key = max(keybase, max(sin_arg_key(th), sin_arg_key(fma((double)(RESTART * TILE), dth, th))));
+            if (rcount == 0) {
+                fast_sincos_core(th, S0, C0);
+                S0 *= amp; C0 *= amp;
+            } else {
+                const double sn = fma(C0, sdT, S0 * cdT);
+                C0 = fma(-S0, sdT, C0 * cdT);
+                S0 = sn;
+            }
+            rcount = (rcount + 1 == REANCHOR) ? 0 : rcount + 1;
+            Sc = S0; Cc = C0;
+        }
+        const double Lt = fma(sl, xc, c0);          // line at the centre of the first block
+        double q[4] = {0.0, 0.0, 0.0, 0.0};
+        mbar_wait(&full[st], par);
+        if (key < MC3B_SIN_KEY_LIMIT) {
+            const double* ft = sf[st];
+#pragma unroll
+            for (int b = 0; b < TILE / BLK; b++) {
+                const double Lc = b == 0 ? Lt : fma(dL16, (double)b, Lt);
+#pragma unroll
+                for (int pp = 0; pp < NP; pp++) {
+                    const double2 f2 = *reinterpret_cast<const double2*>(&ft[b * BLK + 2 * pp]);
+                    const double u = fma(Sc, cp[pp], Lc + f2.x);
+                    const double v = fma(Cc, sp[pp], fma(gs, (double)pp + 0.5, f2.y));
+                    q[(2 * pp) & 3] = fma(u, u, q[(2 * pp) & 3]);
+                    q[(2 * pp + 1) & 3] = fma(v, v, q[(2 * pp + 1) & 3]);
+                }
+                const double sn = fma(Cc, s16, Sc * c16);
+                Cc = fma(-Sc, s16, Cc * c16);
+                Sc = sn;
+            }
+        } else {                                    // guarded chains: library sine per point, raw data
+            double qd = 0.0;
+            const double xt = fma((double)((tb + it) * TILE), dx, x0);
+            const double* dt = a.d + (tb + it) * TILE;
+            for (int i = 0; i < TILE; i++) {
+                const double r = direct(fma((double)i, dx, xt)) - dt[i];
+                qd = fma(r, r, qd);
+            }
+            q[0] = 0.5 * qd;
+        }
+        acc += (q[0] + q[1]) + (q[2] + q[3]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (threadIdx.x == 0 && it >= 1 && it - 1 + NSTAGE < nt) {
+            const int sq = (int)((it - 1) % NSTAGE);
+            mbar_wait(&empty[sq], (uint32_t)(((it - 1) / NSTAGE) & 1));
+            issue(tb + it - 1 + NSTAGE, sq);
+        }
+    }
+
+    acc *= 2.0;
+    if (blockIdx.y == gridDim.y - 1) {              // ragged tail, straight from global memory
+        double t = 0.0;
+        for (int64_t i = nfull * TILE; i < a.n; i++) {
+            const double r = direct(a.x[i]) - a.d[i];
+            t = fma(r, r, t);
+        }
+        acc += t;
+    }
+    const double w0 = a.w[0];
+    if (live) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = acc * (w0 * w0);
+#ifndef MC3B_NO_FUSE_CODE
+    if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32);
+#endif
+}
+
+// out[16 b + 2 p] = -(d[16 b + 8 + p] + d[16 b + 7 - p])/2, out[16 b + 2 p + 1] = -(d[hi] - d[lo])/2
+__global__ void k_fold(const double* __restrict__ d, int64_t nblk16, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nblk16 * 16) return;
+    const int64_t b = i >> 4;
+    const int j = (int)(i & 15), pp = j >> 1;
+    const double lo = d[b * 16 + 7 - pp], hi = d[b * 16 + 8 + pp];
+    out[i] = (j & 1) ? -0.5 * (hi - lo) : -0.5 * (hi + lo);
+}
+
 }  // namespace
+
+int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned groups, unsigned nsplit, cudaStream_t st) {
+    if (work == nullptr) {
+        k_sinefold<false><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a0);
+        MC3B_CHECK_LAUNCH("k_sinefold");
+        return MC3B_OK;
+    }
+    ChisqArgs<double> a = a0;
+    a.consts = work; a.ldc = a.nchains; a.consts_wait = 0;
+    k_fold_consts<<<(unsigned)((a.nchains + 127) / 128), 128, 0, st>>>(a.params, a.ldp, a.nchains, a.x, a.n, work, a.ldc);
+    MC3B_CHECK_LAUNCH("k_fold_consts");
+    static const bool pdl = getenv("MC3B_FOLD_PDL") && atoi(getenv("MC3B_FOLD_PDL")) != 0;
+    if (pdl) {
+        // programmatic dependent launch: the CTAs set up their barriers and start the first
+        // bulk copies while k_fold_consts runs, and wait for it only before reading the constants
+        a.consts_wait = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(groups, nsplit); cfg.blockDim = dim3(WARPS * 32); cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true>, a));
+    } else {
+        k_sinefold<true><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
+    }
+    MC3B_CHECK_LAUNCH("k_sinefold");
+    return MC3B_OK;
+}
+
+int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st) {
+    const int64_t nb = n / 16;
+    if (nb == 0) return MC3B_OK;
+    k_fold<<<(unsigned)((nb * 16 + 255) / 256), 256, 0, st>>>(d, nb, out);
+    MC3B_CHECK_LAUNCH("k_fold");
+    return MC3B_OK;
+}
 
 int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st) {
     if (usig) k_sinegrid<true><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);

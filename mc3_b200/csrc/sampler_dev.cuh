@@ -23,9 +23,14 @@ __device__ __forceinline__ void box_muller(double u1, double u2, double& n0, dou
 // Peer-memory exchange: generation flags (include/mc3b200.h, F_peers).
 // Precondition: every CTA that stored into peers has executed a system fence (after a CTA
 // barrier) before the event that let this thread know the generation is complete.
+// ONE system fence here (it orders everything this thread has observed -- the other CTAs'
+// fenced stores included -- before the flags), then relaxed stores: a release store per
+// peer made every flag wait for the previous flag's round trip over NVLink (~3.3 us per
+// peer: +9 / +15 / +29 us per generation at 2 / 4 / 8 GPUs, profiles/r2_bench_n*.json).
 __device__ __forceinline__ void flags_publish(const mc3b_sampler_t& S, int64_t done) {
+    __threadfence_system();
     for (int p = 0; p < S.world; p++)
-        asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(S.F_peers[p] + S.rank), "l"((long long)done)
+        asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(S.F_peers[p] + S.rank), "l"((long long)done)
                      : "memory");
 }
 // every thread of the CTA calls it (one thread per peer polls, then a CTA barrier)

@@ -182,6 +182,15 @@ class Population:
                 if x[-1] != x[0] and np.max(np.abs(x - ideal)) <= 8*np.finfo(float).eps*np.max(np.abs(x)):
                     self.chisq_model_id = SINUSOID_GRID
                     self.grid = True
+            # with one uncertainty for all points the grid kernel works on point pairs
+            # mirrored about block centres (csrc/chisq_grid.cu k_sinefold): the paired
+            # copy of the data is prepared once here.  MC3B_NO_FOLD=1 disables.
+            self.d_fold = None
+            if self.grid and self.usig and not os.environ.get('MC3B_NO_FOLD'):
+                with torch.cuda.device(self.dev):
+                    self.d_fold = torch.empty_like(self.d_data)
+                    _lib.call('mc3b_fold_data', self.d_data.data_ptr(), self.ndata,
+                              self.d_fold.data_ptr(), _lib.stream_ptr())
             if self.dtype == _lib.F32:
                 self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
                                                 (self.d_x, self.d_data, self.d_invsig))
@@ -429,6 +438,11 @@ class Population:
             o = _lib.ChisqOpts()
             o.plan_chains = self._plan_chains(nb) if self.plan_chains else 0
             o.uniform_sigma = 1 if self.usig else 0
+            if self.d_fold is not None:
+                o.folded = self.d_fold.data_ptr()
+                if not os.environ.get('MC3B_NO_FOLD_CONSTS'):
+                    o.work = self._workspace(('foldk', nb), (_lib.FOLD_WORK, nb)).data_ptr()
+                    self.launches += 1
             if fuse is not None:
                 o.c_off, o.gen, o.zrow0, adv = fuse
                 o.advance = 1 if adv else 0

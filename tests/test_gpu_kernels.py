@@ -520,3 +520,140 @@ def test_population_picks_grid_kernel_only_for_uniform_x(mc3):
     xj = p['x'] + 1e-9*np.sin(np.arange(p['x'].size))
     pop2 = Population(p['data'], p['uncert'], mc3.models.sinusoid, p['params'], [xj], {}, **kw)
     assert not pop2.grid
+
+
+# ---- the mirrored-pair form of the uniform-grid kernel (k_sinefold) ----------------
+def _fold_np(d):
+    """include/mc3b200.h mc3b_fold_data, in numpy."""
+    nb = d.size//16
+    b = d[:nb*16].reshape(nb, 16)
+    lo, hi = b[:, 7::-1], b[:, 8:]
+    out = np.empty((nb, 16))
+    out[:, 0::2] = -0.5*(hi + lo)
+    out[:, 1::2] = -0.5*(hi - lo)
+    return out.ravel()
+
+
+def _run_grid_usig(P, x, data, sigma, folded, rows=False, work=False):
+    from mc3_b200 import _lib
+    dev = torch.device('cuda')
+    nch, n = P.shape[0], x.size
+    dP, dx, dd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (P, x, data))
+    dw = torch.tensor([1.0/sigma], dtype=torch.float64, device=dev)
+    o = _lib.ChisqOpts()
+    o.uniform_sigma = 1
+    if folded:
+        df = torch.full((n,), float('nan'), dtype=torch.float64, device=dev)
+        _lib.call('mc3b_fold_data', dd.data_ptr(), n, df.data_ptr(), _lib.stream_ptr())
+        o.folded = df.data_ptr()
+        if work:
+            wk = torch.empty((_lib.FOLD_WORK, nch), dtype=torch.float64, device=dev)
+            o.work = wk.data_ptr()
+    ns = ctypes.c_int(0)
+    _lib.call('mc3b_model_chisq_plan', nch, n, _lib.F64, ctypes.byref(ns))
+    part = torch.empty((ns.value, nch), dtype=torch.float64, device=dev)
+    _lib.call('mc3b_model_chisq_ex', 4, _lib.F64, dP.data_ptr(), 5, nch, 5, dx.data_ptr(),
+              dd.data_ptr(), dw.data_ptr(), n, part.data_ptr(), nch, ns.value,
+              ctypes.byref(o), _lib.stream_ptr())
+    torch.cuda.synchronize()
+    if rows:
+        return part.cpu().numpy()
+    return part.sum(dim=0).cpu().numpy()
+
+
+def test_fold_data_is_the_documented_layout(mc3):
+    from mc3_b200 import _lib
+    dev = torch.device('cuda')
+    for n in (16, 100, 4099, 100000):
+        d = np.random.RandomState(n).normal(3, 2, n)
+        dd = torch.from_numpy(d).to(dev)
+        out = torch.full((n,), 7.0, dtype=torch.float64, device=dev)
+        _lib.call('mc3b_fold_data', dd.data_ptr(), n, out.data_ptr(), _lib.stream_ptr())
+        got = out.cpu().numpy()
+        nb = n//16*16
+        assert np.array_equal(got[:nb], _fold_np(d))
+        assert np.all(got[nb:] == 7.0)
+
+
+@pytest.mark.parametrize('n,span,offset,snr', [(100000, 10.0, 5.0, 2.0), (65536 + 77, 300.0, 25.0, 1e4),
+                                               (3001, 2.0, 5e4, 1.0), (1 << 20, 5000.0, -3.0, 30.0),
+                                               (130, 1.0, 1.0, 5.0)])
+def test_sinusoid_folded_kernel_matches_oracle(mc3, n, span, offset, snr):
+    """k_sinefold (point pairs mirrored about block centres, one uncertainty for all
+    points) against the per-point evaluation: benign and short periods, offsets far
+    above the noise, high S/N, ragged tails; and against k_sinegrid at 1e-11."""
+    rs = np.random.RandomState(n % 1000 + 5)
+    nch = 192
+    x = np.linspace(0.1*span, 1.1*span, n)
+    truth = np.array([1.3, 0.37*span/10, 0.4, offset, 0.02])
+    sigma = truth[0]/snr
+    data = om.sinusoid(truth, x) + rs.normal(0, sigma, n)
+    P = truth + rs.normal(0, 1, (nch, 5))*np.array([0.05, 1e-4, 0.05, 0.05, 1e-3])/snr
+    if snr <= 10:
+        P[::7, 1] = rs.uniform(2.2, 12, P[::7].shape[0])*(x[1] - x[0])      # a few samples per period
+        P[1::7, 1] = rs.uniform(0.5, 3, P[1::7].shape[0])*span                # less than a period in all
+    got = _run_grid_usig(P, x, data, sigma, True)
+    want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+    np.testing.assert_allclose(got, want, rtol=R64)
+    ref = _run_grid_usig(P, x, data, sigma, False)
+    # (at S/N 1e4 an error of 1e-15 A in the sine is already 1e-11 sigma: both kernels sit
+    # ~1e-11 from the oracle there, on different sides)
+    np.testing.assert_allclose(got, ref, rtol=1e-11 if snr <= 100 else R64)
+    # run-to-run determinism; constants derived once per chain (opts.work) or by every CTA:
+    # same bits; and the library-sine guard for huge arguments
+    assert np.array_equal(got, _run_grid_usig(P, x, data, sigma, True))
+    assert np.array_equal(got, _run_grid_usig(P, x, data, sigma, True, work=True))
+    Pbig = P[:40].copy()
+    Pbig[:, 1] = 1e-9*(x[1] - x[0])*rs.uniform(1, 2, 40)
+    m = min(n, 2000)                 # (the argument's own rounding is ~1e-3 rad here: kernel against kernel)
+    gb = _run_grid_usig(Pbig, x[:m], data[:m], sigma, True)
+    wb = _run_grid_usig(Pbig, x[:m], data[:m], sigma, False)
+    np.testing.assert_allclose(gb, wb, rtol=1e-11)
+
+
+def test_folded_partial_rows_are_the_oracle_over_their_split(mc3):
+    from mc3_b200 import _lib
+    rs = np.random.RandomState(77)
+    nch, n, sigma = 4096, 100000 + 37, 0.5
+    x = np.linspace(0.0, 10.0, n)
+    P = np.column_stack([rs.uniform(0.5, 2, nch), rs.uniform(0.3, 3.0, nch), rs.uniform(-3, 3, nch),
+                         rs.uniform(-1, 1, nch), rs.uniform(-0.1, 0.1, nch)])
+    data = om.sinusoid(P[0], x) + rs.normal(0, sigma, n)
+    got = _run_grid_usig(P, x, data, sigma, True, rows=True)
+    ns = ctypes.c_int(0)
+    bounds = (ctypes.c_int64*(got.shape[0] + 1))()
+    _lib.call('mc3b_model_chisq_splits', nch, n, _lib.F64, bounds, got.shape[0] + 1, ctypes.byref(ns))
+    b = np.array(bounds[:ns.value + 1])
+    for c in (0, 1, nch//2, nch - 1):
+        r2 = ((om.sinusoid(P[c], x) - data)/sigma)**2
+        want = np.array([r2[b[s]:b[s + 1]].sum() for s in range(ns.value)])
+        np.testing.assert_allclose(got[:, c], want, rtol=1e-9, atol=1e-9*want.max())
+        np.testing.assert_allclose(got[:, c].sum(), r2.sum(), rtol=R64)
+
+
+def test_population_uses_the_folded_kernel_for_one_uncertainty(mc3, monkeypatch):
+    """Population prepares the paired copy of the data when the grid kernel applies and
+    the uncertainties are all equal; the run is the same Markov chain as with the
+    per-point kernel up to the rounding of chi-squared (same decisions on this case)."""
+    from mc3_b200.engine import Population
+    from mc3_b200 import workloads
+    w = workloads.config2(n=20000)
+    kw = dict(pstep=w['pstep'], pmin=w['pmin'], pmax=w['pmax'], prior=w['prior'], priorlow=w['priorlow'],
+              priorup=w['priorup'], nchains=256, sampler='demc', fepsilon=w['fepsilon'], nzchain=12, seed=3)
+    pop = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
+    assert pop.grid and pop.usig and pop.d_fold is not None
+    pop.init_population('normal')
+    pop.run(12)
+    monkeypatch.setenv('MC3B_NO_FOLD', '1')
+    pop2 = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
+    assert pop2.d_fold is None
+    pop2.init_population('normal')
+    pop2.run(12)
+    torch.cuda.synchronize()
+    assert torch.equal(pop.zchain, pop2.zchain)
+    np.testing.assert_allclose(pop.log_post.cpu().numpy(), pop2.log_post.cpu().numpy(), rtol=1e-11)
+    np.testing.assert_allclose(pop.Z.cpu().numpy(), pop2.Z.cpu().numpy(), rtol=0, atol=0)
+    unc = w['uncert'].copy()
+    unc[5] *= 1.5
+    pop3 = Population(w['data'], unc, mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
+    assert pop3.grid and not pop3.usig and pop3.d_fold is None
