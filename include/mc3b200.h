@@ -110,7 +110,9 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
  *                per-chain constants of the kernel (wavenumber, the sine/cosine tables of
  *                the pair offsets, block and restart rotations) are then derived once per
  *                chain by a small kernel launched first, instead of by each of the nsplit
- *                CTAs of a chain group.  NULL: every CTA derives them (same bits). */
+ *                CTAs of a chain group.  NULL: every CTA derives them (same bits).
+ * moment         non-NULL (with uniform_sigma, fuse and work; fp64, MC3B_MODEL_SINUSOID_GRID):
+ *                the sufficient-statistics form described at mc3b_moment_t below. */
 struct mc3b_sampler;
 typedef struct mc3b_chisq_opts {
     int64_t plan_chains;
@@ -121,8 +123,42 @@ typedef struct mc3b_chisq_opts {
     int64_t c_off, gen, zrow0;
     const void* folded;
     void* work;
+    const struct mc3b_moment* moment;
 } mc3b_chisq_opts_t;
-#define MC3B_FOLD_WORK 21
+#define MC3B_FOLD_WORK 25
+
+/* Sufficient-statistics form of the uniform-grid sinusoid + line chi-squared (one
+ * uncertainty for all points).  With the data centred on a reference line,
+ * d' = d - (c0ref + slref x), the squares of the pair sums and differences expand to
+ *   chisq sigma^2 = 2 sum_blocks [ Sc (Sc Kcc + 2 Lc Kc - 2 Pe) + Cc (Cc Kss + 2 g Ksd - 2 Po) ]
+ *                 + 2 sum_tiles  [ 64 Lm^2 + 87376 g^2 - 2 Lm M0 - 2 g M1 + M2 ]
+ * where only Pe = sum_p cos(dl_p h) e_p and Po = sum_p sin(dl_p h) o_p touch the data
+ * (ONE multiply-add per point and chain) and M0, M1, M2 are three moments per
+ * 128-point tile.  The result is what is left after sums of size (|s| + |L'| + |d'|)^2
+ * cancel, so its relative error is eps_eff * amp with
+ *   amp = (|A| sqrt(n) + |L'| + sqrt(d2tot))^2 / (sigma^2 chisq),   eps_eff < 3e-15;
+ * the Metropolis epilogue evaluates every chain with amp > amp_max again, point by
+ * point (library sine), and counts it in *guard_hits, so that every chi-squared used
+ * for a decision is within 1e-10 of _chisq.c:111-140 on the same inputs.
+ *   folded  [n]  from mc3b_moment_prepare     tiles  [4 * (n/128)]  likewise
+ *   c0ref, slref   the reference line (any; a least-squares line through the data keeps amp small)
+ *   d2tot   sum of d'^2 over the n points     amp_max  e.g. 4000 (error < 1.2e-11)
+ *   guard_hits  device int32 counter or NULL */
+typedef struct mc3b_moment {
+    const double* folded;
+    const double* tiles;
+    double c0ref, slref, d2tot, amp_max;
+    int32_t* guard_hits;
+} mc3b_moment_t;
+
+/* Chain-independent preparation for mc3b_moment_t: x_i = x0 + i dx.  Per 16-point
+ * block, pair p joins points 7-p and 8+p: folded[16 b + 2 p] = -(d'_hi + d'_lo),
+ * folded[16 b + 2 p + 1] = -(d'_hi - d'_lo); per 128-point tile t,
+ * tiles[4 t ..] = {-2 sum e, -2 (16 sum_b (b - 3.5) sum_p e + sum (p + 1/2) o), sum e^2 + o^2, 0}
+ * with e, o the half sum and half difference of a pair.  Only whole tiles are written. */
+int mc3b_moment_prepare(const double* data, int64_t n, double x0, double dx,
+                        double c0ref, double slref, double* folded, double* tiles,
+                        void* stream);
 
 /* Chain-independent preparation for `folded` above: per block of 16 points, pair
  * p = 0..7 joins points 7-p and 8+p of the block;

@@ -42,14 +42,21 @@ class SamplerStruct(ctypes.Structure):
     ]
 
 
+class MomentStruct(ctypes.Structure):
+    """mc3b_moment_t."""
+    _fields_ = [('folded', c_vp), ('tiles', c_vp), ('c0ref', c_dbl), ('slref', c_dbl),
+                ('d2tot', c_dbl), ('amp_max', c_dbl), ('guard_hits', c_vp)]
+
+
 class ChisqOpts(ctypes.Structure):
     """mc3b_chisq_opts_t."""
     _fields_ = [('plan_chains', c_i64), ('uniform_sigma', c_i32), ('advance', c_i32),
                 ('fuse', ctypes.POINTER(SamplerStruct)), ('fuse_done', c_vp),
-                ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64), ('folded', c_vp), ('work', c_vp)]
+                ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64), ('folded', c_vp), ('work', c_vp),
+                ('moment', ctypes.POINTER(MomentStruct))]
 
 
-FOLD_WORK = 21                    # MC3B_FOLD_WORK
+FOLD_WORK = 25                    # MC3B_FOLD_WORK
 
 
 class DrawsStruct(ctypes.Structure):
@@ -72,6 +79,7 @@ _SIGS = {
                                     c_vp, c_vp, c_i64, c_vp, c_i64, c_int,
                                     ctypes.POINTER(ChisqOpts), c_vp]),
     'mc3b_fold_data': (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),
     'mc3b_chisq_finish': (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,

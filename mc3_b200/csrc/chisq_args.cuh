@@ -44,6 +44,15 @@ struct FuseArgs {
     mc3b_sampler_t S;
 };
 
+// k_sinefold<MOM>: data centred on a reference line, folded and scaled (mc3b_moment_prepare),
+// the per-tile moments, and the guard of the expansion (include/mc3b200.h, mc3b_moment_t)
+struct MomentArgs {
+    const double* folded;           // nullptr: not the moment form
+    const double* tiles;
+    double c0ref, slref, d2tot, amp_max;
+    int32_t* guard_hits;
+};
+
 template <typename T> struct ChisqArgs {
     int nsched;                     // > 0: split y covers tiles [tstart[y], tstart[y+1])
     int32_t tstart[SCHED_MAX + 1];
@@ -54,6 +63,7 @@ template <typename T> struct ChisqArgs {
     const double* consts;           // k_sinefold: per-chain constants [NCONST, ldc] (k_fold_consts) or nullptr
     int64_t ldc;
     int consts_wait;                // launched as a programmatic dependent of k_fold_consts
+    MomentArgs m;
     int64_t n;
     double* partial;
     int64_t ldpartial;
@@ -63,17 +73,14 @@ template <typename T> struct ChisqArgs {
 
 // The Metropolis step itself, compiled once per translation unit: S points to the
 // CTA's shared-memory copy of the sampler description.
-static __device__ __noinline__ void fused_metropolis_tail(const mc3b_sampler_t* S, const double* partial, int64_t ldpartial,
-                                                   int nsplit, int64_t cl, int64_t c_off, int64_t gen,
-                                                   int64_t zrow0) {
-    if (gen < 0) {
-        gen = *S->gen_dev;
-        zrow0 = ((gen + 1) % S->thinning == 0) ? S->M0 + ((gen + 1) / S->thinning - 1) * S->nchains : -1;
-    }
-    const int64_t c = c_off + cl;
-    const double nxt = S->inb[c] ? sum_partials<true>(partial, ldpartial, nsplit, cl) : 0.0;
+static __device__ __noinline__ void fused_metropolis_step(const mc3b_sampler_t* S, double nxt, int64_t c, int64_t gen,
+                                                          int64_t zrow0) {
     metropolis_chain(*S, nxt, gen, zrow0, c);
 }
+
+// Hook between the sum of a chain's partial rows and its Metropolis step; called by
+// every thread of the reducer CTA (it may use CTA barriers).
+struct NoFix { __device__ __forceinline__ void operator()(bool, int64_t, double&) const {} };
 
 // chains_per_cta: chains a CTA covers (its thread t < chains_per_cta owns chain
 // blockIdx.x * chains_per_cta + t of the launch).  `f` must be the kernel
@@ -85,8 +92,9 @@ static __device__ __noinline__ void fused_metropolis_tail(const mc3b_sampler_t* 
 // publish their row with one fire-and-forget reduction (no round trip: an atomic
 // whose result every CTA waited for cost ~10 us per launch over the six waves) and
 // leave; the reducer spins until all nsplit-1 arrivals are in.
+template <class Fix = NoFix>
 __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double* partial, int64_t ldpartial,
-                                                 int64_t nchains, int chains_per_cta) {
+                                                 int64_t nchains, int chains_per_cta, Fix fix = Fix()) {
     __shared__ __align__(16) mc3b_sampler_t sS;
     __shared__ double vbuf[STAGE_DOUBLES];
     __syncthreads();                               // the CTA's partial row is written
@@ -126,8 +134,20 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
     }
     __syncthreads();
     const int64_t cl = (int64_t)blockIdx.x * chains_per_cta + threadIdx.x;
-    if ((int)threadIdx.x < chains_per_cta && cl < nchains)
-        fused_metropolis_tail(&sS, partial, ldpartial, (int)gridDim.y, cl, f.c_off, f.gen, f.zrow0);
+    const bool mine = (int)threadIdx.x < chains_per_cta && cl < nchains;
+    int64_t gen = f.gen, zrow0 = f.zrow0;
+    if (gen < 0) {
+        gen = *sS.gen_dev;
+        zrow0 = ((gen + 1) % sS.thinning == 0) ? sS.M0 + ((gen + 1) / sS.thinning - 1) * sS.nchains : -1;
+    }
+    double nxt = 0.0;
+    bool inb = false;
+    if (mine) {
+        inb = sS.inb[f.c_off + cl] != 0;
+        if (inb) nxt = sum_partials<true>(partial, ldpartial, (int)gridDim.y, cl);
+    }
+    fix(inb, cl, nxt);
+    if (mine) fused_metropolis_step(&sS, nxt, f.c_off + cl, gen, zrow0);
     __syncthreads();
     if (threadIdx.x == 0 && f.advance) {
         // one fence for the CTA's stores (cumulative over the barrier): system scope when they
@@ -150,3 +170,5 @@ using namespace mc3b_chisq;
 int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_sinefold(const ChisqArgs<double>& a, double* work, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st);
+int mc3b_launch_moment_prepare(const double* d, int64_t n, double x0, double dx, double c0ref, double slref,
+                               double* folded, double* tiles, cudaStream_t st);

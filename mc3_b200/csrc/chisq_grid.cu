@@ -240,13 +240,14 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
 // anchor, every REANCHOR-th from fast_sincos_core; 32 block rotations in between.
 // Rotations are stable for any step, so only huge arguments take the direct path.
 // Per-chain constants of the kernel: every CTA of a chain group (105 data splits at
-// config 2) would derive the same 21 numbers through a division and four dependent
+// config 2) would derive the same numbers through a division and four dependent
 // sine/cosine evaluations before it can touch its first tile (ncu, round 2: a third of
 // all warp time).  k_fold_consts derives them once per chain and launch; the CTAs
 // then start with one round of coalesced loads.  Same formulas, same bits.
 namespace fold {
 constexpr int BLK = 16, NP = BLK / 2;
-constexpr int NCONST = 2 * NP + 5;      // k, cp[NP], sp[NP], c16, s16, cdT, sdT
+constexpr int NCONST = 2 * NP + 9;      // k, cp[NP], sp[NP], c16, s16, cdT, sdT, Kcc, Kc2, Kss, Ksd2
+static_assert(NCONST == MC3B_FOLD_WORK, "include/mc3b200.h: MC3B_FOLD_WORK");
 struct Consts { double k, cp[NP], sp[NP], c16, s16, cdT, sdT; };
 __device__ __forceinline__ void derive(double period, double dx, Consts& K) {
     using namespace grid;
@@ -271,27 +272,111 @@ __global__ void __launch_bounds__(128) k_fold_consts(const double* __restrict__ 
     asm volatile("griddepcontrol.launch_dependents;");
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
+    using fold::NP;
     const double x0 = x[0];
     const double dx = (x[n - 1] - x0) / (double)(n - 1);
     fold::Consts K;
     fold::derive(params[c * ldp + 1], dx, K);
     double* o = out + c;
     o[0] = K.k;
+    double kcc = 0.0, kc = 0.0, kss = 0.0, ksd = 0.0;       // sums over the pair offsets (k_sinefold<MOM>)
 #pragma unroll
-    for (int i = 0; i < fold::NP; i++) { o[(1 + i) * ld] = K.cp[i]; o[(1 + fold::NP + i) * ld] = K.sp[i]; }
-    o[(1 + 2 * fold::NP) * ld] = K.c16; o[(2 + 2 * fold::NP) * ld] = K.s16;
-    o[(3 + 2 * fold::NP) * ld] = K.cdT; o[(4 + 2 * fold::NP) * ld] = K.sdT;
+    for (int i = 0; i < NP; i++) {
+        o[(1 + i) * ld] = K.cp[i]; o[(1 + NP + i) * ld] = K.sp[i];
+        kcc = fma(K.cp[i], K.cp[i], kcc); kc += K.cp[i];
+        kss = fma(K.sp[i], K.sp[i], kss); ksd = fma(K.sp[i], (double)i + 0.5, ksd);
+    }
+    o[(1 + 2 * NP) * ld] = K.c16; o[(2 + 2 * NP) * ld] = K.s16;
+    o[(3 + 2 * NP) * ld] = K.cdT; o[(4 + 2 * NP) * ld] = K.sdT;
+    o[(5 + 2 * NP) * ld] = kcc; o[(6 + 2 * NP) * ld] = 2.0 * kc;
+    o[(7 + 2 * NP) * ld] = kss; o[(8 + 2 * NP) * ld] = 2.0 * ksd;
 }
+
+// ---- MOM: the same sum from sufficient statistics -------------------------------------
+// Expanding the squares of u and v over a block's eight pairs,
+//   sum_p u_p^2 + v_p^2 = Sc (Sc Kcc + 2 Lc Kc - 2 Pe) + Cc (Cc Kss + 2 g Ksd - 2 Po)
+//                         + [8 Lc^2 + 170 g^2 - 2 Lc E1 - 2 g O1 + E2 + O2]
+//   Pe = sum_p cp_p e_p,  Po = sum_p sp_p o_p,  Kcc = sum cp^2, Kc = sum cp, Kss = sum sp^2, Ksd = sum sp dl
+// only Pe and Po touch the data: ONE FMA per point; the bracket needs the data only
+// through three moments per 128-point tile (prepared once by mc3b_moment_prepare,
+// like the pairs themselves, which it stores centred on a reference line and scaled by
+// -2).  28 FP64 instructions per 16-point block: 1.75 per chain-point.
+// The price: chi-squared is what is left after sums of size (|s| + |L'| + |d'|)^2 cancel,
+// so its relative error is eps_eff amp, amp = (|s|max + |L'| + |d'|)^2 / (sigma^2 chisq),
+// eps_eff < 3e-15 (profiles/moment_error.py, against long double).  The Metropolis
+// epilogue therefore checks amp <= amp_max for every chain (MomentFix below) and
+// re-evaluates the chains that fail it point by point, so that every chi-squared that
+// leaves the kernel is within the 1e-10 contract; the host watches the count and
+// returns to k_sinefold<MOM=false> when it is not rare (high signal-to-noise data).
+struct MomentFix {
+    const ChisqArgs<double>& a;
+    // `act`: this thread owns a chain whose proposal is inside the bounds; nxt = its data chi-squared
+    __device__ __forceinline__ void operator()(bool act, int64_t cl, double& nxt) const {
+        const MomentArgs& m = a.m;
+        const double w0 = a.w[0];
+        bool bad = false;
+        const double* p = a.params + cl * a.ldp;
+        if (act) {
+            const double n = (double)a.n, x0 = a.x[0];
+            const double dx = (a.x[a.n - 1] - x0) / (n - 1.0);
+            const double c0 = p[3] - m.c0ref, sl = p[4] - m.slref;
+            const double lm = fma(sl, fma(0.5 * (n - 1.0), dx, x0), c0), g = sl * dx;
+            const double l2 = n * (lm * lm + g * g * (n * n - 1.0) * (1.0 / 12.0));
+            const double mag = fabs(p[0]) * sqrt(n) + sqrt(l2) + sqrt(m.d2tot);
+            bad = !(mag * mag * (w0 * w0) <= m.amp_max * nxt);        // NaN: exact path too
+        }
+        if (!__syncthreads_or(bad)) return;
+        // rare: the flagged chains one at a time, in thread order, the whole CTA over the data
+        __shared__ double prm[5], red[WARPS];
+        __shared__ uint32_t mask[WARPS];
+        const uint32_t bal = __ballot_sync(0xffffffffu, bad);
+        if ((threadIdx.x & 31) == 0) mask[threadIdx.x >> 5] = bal;
+        __syncthreads();
+        for (int w = 0; w < WARPS; w++) {
+            uint32_t mk = mask[w];
+            while (mk) {
+                const int t = w * 32 + __ffs(mk) - 1;
+                mk &= mk - 1;
+                if ((int)threadIdx.x == t) {
+                    for (int j = 0; j < 5; j++) prm[j] = p[j];
+                    if (m.guard_hits) atomicAdd(m.guard_hits, 1);
+                }
+                __syncthreads();
+                const double amp = prm[0], k = 6.283185307179586476925287 / prm[1], ph = prm[2], c0 = prm[3], sl = prm[4];
+                double q = 0.0;
+                for (int64_t i = threadIdx.x; i < a.n; i += WARPS * 32) {
+                    const double x = a.x[i];
+                    const double r = fma(amp, sin(fma(x, k, ph)), fma(sl, x, c0)) - a.d[i];
+                    q = fma(r, r, q);
+                }
+                for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+                __syncthreads();
+                if ((int)threadIdx.x == t) {
+                    double tot = 0.0;
+                    for (int j = 0; j < WARPS; j++) tot += red[j];
+                    nxt = tot * (w0 * w0);
+                }
+                __syncthreads();
+            }
+        }
+    }
+};
 
 #ifndef MC3B_FOLD_MINB
 #define MC3B_FOLD_MINB 4
 #endif
-template <bool PRE>
+#ifndef MC3B_MOM_ACC
+#define MC3B_MOM_ACC 2
+#endif
+template <bool PRE, bool MOM>
 __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqArgs<double> a) {
     using namespace grid;
     using fold::BLK; using fold::NP;
+    static_assert(PRE || !MOM, "the moment form takes its constants from k_fold_consts");
     asm volatile("griddepcontrol.launch_dependents;");
     __shared__ __align__(128) double sf[NSTAGE][TILE];
+    __shared__ __align__(32) double sm[MOM ? NSTAGE : 1][4];        // tile moments
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,9 +395,11 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
         mbar_fence_init();
     }
     __syncthreads();
+    const double* folded = MOM ? a.m.folded : a.fold;
     auto issue = [&](int64_t t, int s) {
-        mbar_expect_tx(&full[s], TILE * sizeof(double));
-        bulk_g2s(sf[s], a.fold + t * TILE, TILE * sizeof(double), &full[s]);
+        mbar_expect_tx(&full[s], (TILE + (MOM ? 4 : 0)) * sizeof(double));
+        bulk_g2s(sf[s], folded + t * TILE, TILE * sizeof(double), &full[s]);
+        if constexpr (MOM) bulk_g2s(sm[s], a.m.tiles + t * 4, 4 * sizeof(double), &full[s]);
     };
     if (threadIdx.x == 0)
         for (int s = 0; s < NSTAGE && s < nt; s++) issue(tb + s, s);
@@ -321,7 +408,10 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     const double dx = (a.x[a.n - 1] - x0) / (double)(a.n - 1);
     const double* p = a.params + c * a.ldp;
     const double amp = p[0], ph = p[2], c0 = p[3], sl = p[4];
+    // MOM: the line relative to the reference line the data were centred on
+    const double c0r = MOM ? c0 - a.m.c0ref : c0, slr = MOM ? sl - a.m.slref : sl;
     fold::Consts K;
+    double Kcc = 0.0, Kc2 = 0.0, Kss = 0.0, gK = 0.0;
     if constexpr (PRE) {
         if (a.consts_wait) asm volatile("griddepcontrol.wait;" ::: "memory");   // k_fold_consts has completed
         const double* kc = a.consts + c;
@@ -330,6 +420,10 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
         for (int i = 0; i < NP; i++) { K.cp[i] = kc[(1 + i) * a.ldc]; K.sp[i] = kc[(1 + NP + i) * a.ldc]; }
         K.c16 = kc[(1 + 2 * NP) * a.ldc]; K.s16 = kc[(2 + 2 * NP) * a.ldc];
         K.cdT = kc[(3 + 2 * NP) * a.ldc]; K.sdT = kc[(4 + 2 * NP) * a.ldc];
+        if constexpr (MOM) {
+            Kcc = kc[(5 + 2 * NP) * a.ldc]; Kc2 = kc[(6 + 2 * NP) * a.ldc];
+            Kss = kc[(7 + 2 * NP) * a.ldc]; gK = kc[(8 + 2 * NP) * a.ldc];
+        }
     } else {
         fold::derive(p[1], dx, K);
     }
@@ -337,9 +431,10 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     const double (&cp)[NP] = K.cp;
     const double (&sp)[NP] = K.sp;
     const double dth = k * dx;
-    double gs = sl * dx;
+    double gs = slr * dx;
     double dL16 = (double)BLK * gs;
     asm volatile("" : "+d"(gs), "+d"(dL16));
+    gK *= gs;                                       // 2 g Ksd
     const int keybase = sin_arg_key((double)(RESTART * TILE) * dth) >= MC3B_SIN_KEY_LIMIT ? MC3B_SIN_KEY_LIMIT : 0;
     auto direct = [&](double x) { return fma(amp, sin(fma(x, k, ph)), fma(sl, x, c0)); };
 
@@ -365,7 +460,7 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
             rcount = (rcount + 1 == REANCHOR) ? 0 : rcount + 1;
             Sc = S0; Cc = C0;
         }
-        const double Lt = fma(sl, xc, c0);          // line at the centre of the first block
+        const double Lt = fma(slr, xc, c0r);        // line at the centre of the first block
         double q[4] = {0.0, 0.0, 0.0, 0.0};
         mbar_wait(&full[st], par);
         if (key < MC3B_SIN_KEY_LIMIT) {
@@ -373,17 +468,45 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
 #pragma unroll
             for (int b = 0; b < TILE / BLK; b++) {
                 const double Lc = b == 0 ? Lt : fma(dL16, (double)b, Lt);
+                if constexpr (!MOM) {
 #pragma unroll
-                for (int pp = 0; pp < NP; pp++) {
-                    const double2 f2 = *reinterpret_cast<const double2*>(&ft[b * BLK + 2 * pp]);
-                    const double u = fma(Sc, cp[pp], Lc + f2.x);
-                    const double v = fma(Cc, sp[pp], fma(gs, (double)pp + 0.5, f2.y));
-                    q[(2 * pp) & 3] = fma(u, u, q[(2 * pp) & 3]);
-                    q[(2 * pp + 1) & 3] = fma(v, v, q[(2 * pp + 1) & 3]);
+                    for (int pp = 0; pp < NP; pp++) {
+                        const double2 f2 = *reinterpret_cast<const double2*>(&ft[b * BLK + 2 * pp]);
+                        const double u = fma(Sc, cp[pp], Lc + f2.x);
+                        const double v = fma(Cc, sp[pp], fma(gs, (double)pp + 0.5, f2.y));
+                        q[(2 * pp) & 3] = fma(u, u, q[(2 * pp) & 3]);
+                        q[(2 * pp + 1) & 3] = fma(v, v, q[(2 * pp + 1) & 3]);
+                    }
+                } else {
+                    constexpr int NA = MC3B_MOM_ACC;                        // partial sums per block (ILP)
+                    double pe[NA], po[NA];
+#pragma unroll
+                    for (int i = 0; i < NA; i++) { pe[i] = 0.0; po[i] = 0.0; }
+                    pe[0] = Lc * Kc2; po[0] = gK;                           // 2 Lc Kc - 2 Pe ; 2 g Ksd - 2 Po
+#pragma unroll
+                    for (int pp = 0; pp < NP; pp++) {
+                        const double2 f2 = *reinterpret_cast<const double2*>(&ft[b * BLK + 2 * pp]);
+                        pe[pp % NA] = fma(cp[pp], f2.x, pe[pp % NA]);
+                        po[pp % NA] = fma(sp[pp], f2.y, po[pp % NA]);
+                    }
+#pragma unroll
+                    for (int i = NA / 2; i > 0; i >>= 1)
+#pragma unroll
+                        for (int j = 0; j < i; j++) { pe[j] += pe[j + i]; po[j] += po[j + i]; }
+                    q[0] = fma(Sc, fma(Sc, Kcc, pe[0]), q[0]);
+                    q[1] = fma(Cc, fma(Cc, Kss, po[0]), q[1]);
                 }
                 const double sn = fma(Cc, s16, Sc * c16);
                 Cc = fma(-Sc, s16, Cc * c16);
                 Sc = sn;
+            }
+            if constexpr (MOM) {
+                // line and data terms of the whole tile from its three moments:
+                //   64 Lm^2 + 87376 g^2 - 2 Lm M0 - 2 g M1 + M2,  Lm = line at the tile centre
+                const double4 mo = *reinterpret_cast<const double4*>(sm[st]);
+                const double Lm = fma(gs, 56.0, Lt);
+                q[2] = fma(Lm, fma(Lm, 64.0, mo.x), mo.z);
+                q[3] = gs * fma(gs, 87376.0, mo.y);
             }
         } else {                                    // guarded chains: library sine per point, raw data
             double qd = 0.0;
@@ -417,7 +540,8 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     const double w0 = a.w[0];
     if (live) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = acc * (w0 * w0);
 #ifndef MC3B_NO_FUSE_CODE
-    if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32);
+    if constexpr (MOM) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32, MomentFix{a});
+    else if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32);
 #endif
 }
 
@@ -431,11 +555,48 @@ __global__ void k_fold(const double* __restrict__ d, int64_t nblk16, double* __r
     out[i] = (j & 1) ? -0.5 * (hi - lo) : -0.5 * (hi + lo);
 }
 
+// mc3b_moment_prepare: one warp per 128-point tile; lane l holds pairs 2 (l & 3), +1 of
+// block l >> 2.  d' = d - (c0ref + slref x_i); folded[.] = -2 e, -2 o (e, o = half sum and
+// half difference of a pair); tiles[t] = {-2 sum e, -2 (16 sum_b (b - 3.5) E1_b + sum dl o),
+// sum e^2 + o^2, 0}.  Fixed-order shuffles: same bits on every run.
+__global__ void __launch_bounds__(128) k_moment_prepare(const double* __restrict__ d, int64_t ntiles, double x0, double dx,
+                                                        double c0ref, double slref, double* __restrict__ folded,
+                                                        double* __restrict__ tiles) {
+    const int64_t t = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (t >= ntiles) return;
+    const int lane = threadIdx.x & 31, b = lane >> 2;
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pp = 2 * (lane & 3) + h;
+        const int64_t ilo = t * 128 + b * 16 + 7 - pp, ihi = t * 128 + b * 16 + 8 + pp;
+        const double lo = d[ilo] - fma(slref, fma((double)ilo, dx, x0), c0ref);
+        const double hi = d[ihi] - fma(slref, fma((double)ihi, dx, x0), c0ref);
+        const double e = 0.5 * (hi + lo), o = 0.5 * (hi - lo);
+        folded[t * 128 + b * 16 + 2 * pp] = -2.0 * e;
+        folded[t * 128 + b * 16 + 2 * pp + 1] = -2.0 * o;
+        m0 += e;
+        m1 += fma(16.0 * ((double)b - 3.5), e, ((double)pp + 0.5) * o);
+        m2 += fma(e, e, o * o);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, s);
+        m1 += __shfl_xor_sync(0xffffffffu, m1, s);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, s);
+    }
+    if (lane == 0) {
+        double4 o4 = make_double4(-2.0 * m0, -2.0 * m1, m2, 0.0);
+        *reinterpret_cast<double4*>(tiles + t * 4) = o4;
+    }
+}
+
 }  // namespace
 
 int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned groups, unsigned nsplit, cudaStream_t st) {
+    const bool mom = a0.m.folded != nullptr;
     if (work == nullptr) {
-        k_sinefold<false><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a0);
+        if (mom) { mc3b_set_error("the moment form needs the constants workspace (opts.work)"); return MC3B_ERR_ARG; }
+        k_sinefold<false, false><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a0);
         MC3B_CHECK_LAUNCH("k_sinefold");
         return MC3B_OK;
     }
@@ -443,7 +604,7 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
     a.consts = work; a.ldc = a.nchains; a.consts_wait = 0;
     k_fold_consts<<<(unsigned)((a.nchains + 127) / 128), 128, 0, st>>>(a.params, a.ldp, a.nchains, a.x, a.n, work, a.ldc);
     MC3B_CHECK_LAUNCH("k_fold_consts");
-    static const bool pdl = getenv("MC3B_FOLD_PDL") && atoi(getenv("MC3B_FOLD_PDL")) != 0;
+    static const bool pdl = !(getenv("MC3B_FOLD_PDL") && atoi(getenv("MC3B_FOLD_PDL")) == 0);
     if (pdl) {
         // programmatic dependent launch: the CTAs set up their barriers and start the first
         // bulk copies while k_fold_consts runs, and wait for it only before reading the constants
@@ -454,11 +615,23 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true>, a));
+        if (mom) MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true, true>, a));
+        else MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true, false>, a));
+    } else if (mom) {
+        k_sinefold<true, true><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
     } else {
-        k_sinefold<true><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
+        k_sinefold<true, false><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
     }
     MC3B_CHECK_LAUNCH("k_sinefold");
+    return MC3B_OK;
+}
+
+int mc3b_launch_moment_prepare(const double* d, int64_t n, double x0, double dx, double c0ref, double slref,
+                               double* folded, double* tiles, cudaStream_t st) {
+    const int64_t nt = n / 128;
+    if (nt == 0) return MC3B_OK;
+    k_moment_prepare<<<(unsigned)((nt + 3) / 4), 128, 0, st>>>(d, nt, x0, dx, c0ref, slref, folded, tiles);
+    MC3B_CHECK_LAUNCH("k_moment_prepare");
     return MC3B_OK;
 }
 

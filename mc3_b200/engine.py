@@ -148,6 +148,7 @@ class Population:
         data = np.ascontiguousarray(data, dtype=np.double)
         uncert = np.ascontiguousarray(uncert, dtype=np.double)
         self.host_data = data              # whole series (best-fit residual statistics)
+        self.host_uncert0 = float(uncert.flat[0]) if uncert.size else 1.0
         self.ndata_total = data.size
         lo, hi = 0, data.size
         if self.shard == 'data':
@@ -191,6 +192,44 @@ class Population:
                     self.d_fold = torch.empty_like(self.d_data)
                     _lib.call('mc3b_fold_data', self.d_data.data_ptr(), self.ndata,
                               self.d_fold.data_ptr(), _lib.stream_ptr())
+            # ... and, inside the generation loop, on sufficient statistics of those pairs
+            # (k_sinefold<MOM>, one multiply-add per point; include/mc3b200.h mc3b_moment_t):
+            # the data are centred on their least-squares line first, which keeps the
+            # cancellation of the expansion at (signal/noise)^2.  A guard in the kernel
+            # re-evaluates every chain the expansion is not accurate enough for; when that
+            # is not rare (_moment_policy) the population returns to the pair kernel.
+            # MC3B_NO_MOMENT=1 disables.
+            self.moment = None
+            self.use_moment = False
+            if self.d_fold is not None and self.shard == 'chains' and x.size >= 256 \
+                    and not os.environ.get('MC3B_NO_MOMENT') and not os.environ.get('MC3B_NO_FUSE'):
+                with torch.cuda.device(self.dev):
+                    # least-squares line through the data and the sum of squares about it,
+                    # on the device (a few small kernels and one read of three numbers)
+                    xm, dm = self.d_x.mean(), self.d_data.mean()
+                    xc = self.d_x - xm
+                    slr_t = torch.dot(xc, self.d_data - dm)/torch.dot(xc, xc)
+                    c0r_t = dm - slr_t*xm
+                    res = self.d_data - (c0r_t + slr_t*self.d_x)
+                    c0r, slr, d2tot = (float(v) for v in torch.stack([c0r_t, slr_t, torch.dot(res, res)]).cpu())
+                    self.d_mfold = torch.zeros_like(self.d_data)
+                    self.d_mtiles = torch.zeros((x.size//128, 4), **f64)
+                    self.guard_hits = torch.zeros(1, dtype=torch.int32, device=self.dev)
+                    _lib.call('mc3b_moment_prepare', self.d_data.data_ptr(), self.ndata, float(x[0]),
+                              float((x[-1] - x[0])/(x.size - 1)), c0r, slr,
+                              self.d_mfold.data_ptr(), self.d_mtiles.data_ptr(), _lib.stream_ptr())
+                M = _lib.MomentStruct()
+                M.folded, M.tiles = self.d_mfold.data_ptr(), self.d_mtiles.data_ptr()
+                M.c0ref, M.slref, M.d2tot = c0r, slr, d2tot
+                M.amp_max = float(os.environ.get('MC3B_MOMENT_AMP', 4000.0))
+                M.guard_hits = self.guard_hits.data_ptr()
+                self.moment = M
+                self.use_moment = True
+                self._guard_log = []          # (generation, ring slot) per run() call, oldest first
+                self._guard_seen = (0, 0)     # (generation, hits) of the last record evaluated
+                self._guard_pin = torch.zeros(4, dtype=torch.int32).pin_memory()
+                self._guard_ev = [torch.cuda.Event() for _ in range(4)]
+                self._guard_n = 0
             if self.dtype == _lib.F32:
                 self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
                                                 (self.d_x, self.d_data, self.d_invsig))
@@ -440,9 +479,11 @@ class Population:
             o.uniform_sigma = 1 if self.usig else 0
             if self.d_fold is not None:
                 o.folded = self.d_fold.data_ptr()
-                if not os.environ.get('MC3B_NO_FOLD_CONSTS'):
+                if not os.environ.get('MC3B_NO_FOLD_CONSTS') or (fuse is not None and self.use_moment):
                     o.work = self._workspace(('foldk', nb), (_lib.FOLD_WORK, nb)).data_ptr()
                     self.launches += 1
+                if fuse is not None and self.use_moment:
+                    o.moment = ctypes.pointer(self.moment)
             if fuse is not None:
                 o.c_off, o.gen, o.zrow0, adv = fuse
                 o.advance = 1 if adv else 0
@@ -659,6 +700,8 @@ class Population:
         block of generations."""
         if ngen <= 0:
             return
+        if getattr(self, 'use_moment', False):
+            self._moment_policy()
         if use_graph is None:
             # A generation with >= ~0.3 ms of device work hides its three host
             # launches completely: skip the capture (10-15 ms) and run eagerly.
@@ -715,6 +758,41 @@ class Population:
             self._graph.replay()
         self.launches += ngen*self._graph_launches
         self.gen += ngen
+
+    def _moment_policy(self):
+        """Decide, at the start of a run() call, whether the generation loop keeps the
+        sufficient-statistics kernel.  Deterministic: the decision at this call uses the
+        guard count recorded at the end of the call before the previous one (its copy has
+        long landed, so the host does not stall), i.e. it depends on generation
+        boundaries, not on timing.  Before the first generation the amplification is
+        estimated from the best chi-squared of the initial population."""
+        M = self.moment
+        if self.gen == 0 and not self._guard_log and np.isfinite(self.best_log_post0):
+            n, w0 = self.ndata, 1.0/float(self.host_uncert0)
+            mag = abs(float(self.bestp0[0]))*np.sqrt(n) + np.sqrt(M.d2tot)
+            if mag*mag*w0*w0 > 0.5*M.amp_max*max(-2.0*self.best_log_post0, 1e-300):
+                self._moment_off()
+                return
+        while len(self._guard_log) >= 2:
+            gen, slot = self._guard_log.pop(0)
+            self._guard_ev[slot].synchronize()
+            g0, h0 = self._guard_seen
+            hits = int(self._guard_pin[slot])
+            if gen > g0 and (hits - h0) > 1e-3*self.nlocal*(gen - g0):
+                self._moment_off()
+                return
+            self._guard_seen = (gen, hits)
+        slot = self._guard_n % 4
+        self._guard_n += 1
+        self._guard_pin[slot:slot + 1].copy_(self.guard_hits, non_blocking=True)
+        self._guard_ev[slot].record()
+        self._guard_log.append((self.gen, slot))
+
+    def _moment_off(self):
+        self.use_moment = False
+        self._guard_log = []
+        self._graph = None
+        self._block_graph = None
 
     # ------------------------------------------------------------------
     # replay of the reference's recorded stream (sequential chain order)

@@ -34,13 +34,18 @@ def timeit(fn, reps=300):
 P = pop.nextp[:4096]
 g = pop.gen
 print('k_propose (host-driven gen)      %8.2f us' % timeit(lambda: _lib.call('mc3b_propose', ctypes.byref(pop.S), g, pop.zsize(), 0, 4096, st)))
-print('model kernel alone               %8.2f us' % timeit(lambda: pop.data_chisq(P)))
+print('moment form in use:', getattr(pop, 'use_moment', False))
+print('pair kernel alone (k_fold_consts + k_sinefold) %8.2f us' % timeit(lambda: pop.data_chisq(P)))
 zr = pop.M0 + 10*4096
 
 
 def fused():
     pop.data_chisq(P, fuse=(0, g, -1, False))
-print('model kernel + fused Metropolis  %8.2f us' % timeit(fused))
+print('generation kernel + fused Metropolis  %8.2f us' % timeit(fused))
+if getattr(pop, 'use_moment', False):
+    pop.use_moment = False
+    print('pair kernel + fused Metropolis       %8.2f us' % timeit(fused))
+    pop.use_moment = True
 part, ld, ns = pop.data_chisq(P)
 print('k_metropolis alone               %8.2f us' % timeit(lambda: _lib.call('mc3b_metropolis', ctypes.byref(pop.S), part.data_ptr(), ld, ns, 0, g, -1, 0, 4096, st)))
 print('k_advance alone                  %8.2f us' % timeit(lambda: _lib.call('mc3b_advance', ctypes.byref(pop.S), st)))

@@ -1,0 +1,174 @@
+"""GPU parity tests of the sufficient-statistics form of the uniform-grid sinusoid kernel
+(csrc/chisq_grid.cu k_sinefold<MOM>, include/mc3b200.h mc3b_moment_t) against the
+per-point evaluation the reference performs (src_c/_chisq.c:111-140 on the model values
+of the numpy sinusoid).  All calls go through the C ABI."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'profiles'))
+from oracle import kernels as ok            # noqa: E402
+from oracle import models as om             # noqa: E402
+
+pytestmark = pytest.mark.gpu
+R64 = 1e-10
+
+
+@pytest.fixture(scope='module')
+def mc3():
+    import mc3_b200
+    return mc3_b200
+
+
+def test_moment_prepare_matches_numpy(mc3):
+    from mc3_b200 import _lib
+    import moment_error as me
+    dev = torch.device('cuda')
+    rs = np.random.RandomState(2)
+    for n in (128, 1000, 100000):
+        x0, dx = 0.3, 1e-4
+        d = 5.0 - 0.2*(x0 + dx*np.arange(n)) + rs.normal(0, 0.5, n)
+        c0r, slr = 4.9, -0.19
+        f, mom, _ = me.prepare(d, x0, dx, c0r, slr)
+        dd = torch.from_numpy(d).to(dev)
+        df = torch.full((n,), 7.0, dtype=torch.float64, device=dev)
+        dt = torch.zeros((n//128, 4), dtype=torch.float64, device=dev)
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n, x0, dx, c0r, slr, df.data_ptr(),
+                  dt.data_ptr(), _lib.stream_ptr())
+        nt = n//128*128
+        np.testing.assert_allclose(df.cpu().numpy()[:nt], f, rtol=1e-13, atol=1e-14)
+        assert np.all(df.cpu().numpy()[nt:] == 7.0)
+        got = dt.cpu().numpy()
+        want = np.column_stack([-2*mom[:, 0], -2*mom[:, 1], mom[:, 2], np.zeros(n//128)])
+        np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-11)
+
+
+def _population(mc3, n, snr, offset, nchains=256, seed=5, **kw):
+    from mc3_b200.engine import Population
+    rs = np.random.RandomState(seed)
+    x = np.linspace(0.0, 10.0, n)
+    truth = np.array([1.0, 2.5, 0.3, offset, -0.2])
+    sigma = truth[0]/snr
+    data = om.sinusoid(truth, x) + rs.normal(0, sigma, n)
+    step = np.array([1e-2, 1e-3, 1e-2, 1e-2, 1e-3])/max(1.0, snr/2)
+    pop = Population(data, np.full(n, sigma), mc3.models.sinusoid, truth*(1 + 1e-3/snr), [x], {},
+                     pstep=step, pmin=np.array([0.0, 1.0, -np.pi, -1e9, -10.0]),
+                     pmax=np.array([50.0, 5.0, np.pi, 1e9, 10.0]),
+                     prior=np.array([0.0, 2.5, 0.0, 0.0, 0.0]), priorlow=np.array([0.0, 0.1, 0.0, 0.0, 0.0]),
+                     priorup=np.array([0.0, 0.2, 0.0, 0.0, 0.0]),
+                     nchains=nchains, sampler='demc', fepsilon=0.01, nzchain=40, seed=seed, **kw)
+    return pop, x, data, sigma
+
+
+def _one_generation(pop, gen):
+    """host-driven generation `gen`; returns (proposals, data chi-squared from the partial rows,
+    in-bounds flags, chi-squared of every chain before and after)"""
+    before = pop.chisq_cur.clone()
+    pop._generation(gen)
+    torch.cuda.synchronize()
+    nb = pop.nlocal
+    part = [v for k, v in pop._work.items() if k[0] == 'part' and k[1] == nb][0]
+    return (pop.nextp.cpu().numpy(), part.sum(dim=0).cpu().numpy(), pop.inb.cpu().numpy() != 0,
+            before.cpu().numpy(), pop.chisq_cur.cpu().numpy())
+
+
+@pytest.mark.parametrize('n,snr,offset', [(100000, 2.0, 5.0), (20000 + 77, 20.0, 5e3), (4096, 0.5, -3.0)])
+def test_moment_kernel_matches_oracle(mc3, n, snr, offset):
+    """Low and moderate signal-to-noise: the expansion is accurate (no chain trips the
+    guard); its partial rows sum to the oracle's chi-squared and the Metropolis step
+    used exactly that value."""
+    pop, x, data, sigma = _population(mc3, n, snr, offset)
+    assert pop.use_moment
+    pop.init_population('normal')
+    pop.gen_dev.fill_(0)
+    for gen in range(3):
+        P, got, inb, before, after = _one_generation(pop, gen)
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+        np.testing.assert_allclose(got[inb], want[inb], rtol=R64)
+        prior = ((P[:, 1] - 2.5)/np.where(P[:, 1] > 2.5, 0.2, 0.1))**2
+        moved = after != before
+        assert moved.any()
+        np.testing.assert_allclose(after[moved], (want + prior)[moved], rtol=R64)
+    assert int(pop.guard_hits.item()) == 0
+
+
+def test_moment_guard_reevaluates_chains_point_by_point(mc3, monkeypatch):
+    """High signal-to-noise: chains near the mode amplify the rounding of the expansion
+    beyond the contract; the guard must catch every one of them (the accepted values
+    equal the oracle's to 1e-10), count them, and the policy must leave the moment form."""
+    monkeypatch.setenv('MC3B_MOMENT_AMP', '4000')
+    pop, x, data, sigma = _population(mc3, 20000, 3000.0, 7.0, nchains=128)
+    assert pop.moment is not None
+    pop.init_population('normal')
+    pop.use_moment = True                    # (the a-priori estimate would have turned it off: see below)
+    pop.gen_dev.fill_(0)
+    hits = 0
+    for gen in range(3):
+        P, got, inb, before, after = _one_generation(pop, gen)
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+        prior = ((P[:, 1] - 2.5)/np.where(P[:, 1] > 2.5, 0.2, 0.1))**2
+        moved = after != before
+        np.testing.assert_allclose(after[moved], (want + prior)[moved], rtol=R64)
+        n_hits = int(pop.guard_hits.item())
+        assert n_hits > hits
+        hits = n_hits
+    # the policy: a fresh population of the same problem never starts in the moment form ...
+    pop2, *_ = _population(mc3, 20000, 3000.0, 7.0, nchains=128)
+    pop2.init_population('normal')
+    pop2.run(2)
+    assert not pop2.use_moment
+    # ... and one that is forced into it leaves it after the guard has fired
+    pop.gen = 3
+    for _ in range(4):
+        pop.run(1, use_graph=False)
+    torch.cuda.synchronize()
+    assert not pop.use_moment
+
+
+def test_population_moment_and_pair_kernels_walk_the_same_chain(mc3, monkeypatch):
+    from mc3_b200 import workloads
+    from mc3_b200.engine import Population
+    w = workloads.config2(n=30000)
+    kw = dict(pstep=w['pstep'], pmin=w['pmin'], pmax=w['pmax'], prior=w['prior'], priorlow=w['priorlow'],
+              priorup=w['priorup'], nchains=512, sampler='demc', fepsilon=w['fepsilon'], nzchain=30, seed=11)
+    runs = []
+    for env in (None, 'MC3B_NO_MOMENT'):
+        if env:
+            monkeypatch.setenv(env, '1')
+        pop = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
+        assert pop.use_moment == (env is None)
+        pop.init_population('normal')
+        pop.run(30)
+        torch.cuda.synchronize()
+        runs.append((pop.zchain.cpu().numpy(), pop.log_post.cpu().numpy(), pop.Z.cpu().numpy(),
+                     pop.counters()['numaccept']))
+        assert pop.use_moment == (env is None)
+    assert np.array_equal(runs[0][0], runs[1][0])
+    assert runs[0][3] == runs[1][3]
+    np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-11)
+    assert np.array_equal(runs[0][2], runs[1][2])
+
+
+def test_moment_run_is_deterministic_and_graph_equals_eager(mc3):
+    from mc3_b200 import workloads
+    from mc3_b200.engine import Population
+    w = workloads.config2(n=20000)
+    kw = dict(pstep=w['pstep'], pmin=w['pmin'], pmax=w['pmax'], prior=w['prior'], priorlow=w['priorlow'],
+              priorup=w['priorup'], nchains=256, sampler='demc', fepsilon=w['fepsilon'], nzchain=16, seed=4)
+    outs = []
+    for graph in (True, True, False):
+        pop = Population(w['data'], w['uncert'], mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
+        pop.init_population('normal')
+        for _ in range(4):
+            pop.run(4, use_graph=graph)
+        torch.cuda.synchronize()
+        assert pop.use_moment
+        outs.append((pop.Z.cpu().numpy(), pop.log_post.cpu().numpy()))
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
