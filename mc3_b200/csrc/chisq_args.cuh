@@ -125,11 +125,13 @@ __device__ __forceinline__ void fused_metropolis(const FuseArgs& f, const double
         }
         int32_t* ifr = reinterpret_cast<int32_t*>(vbuf + 7 * MAXP);
         for (int i = threadIdx.x; i < nf; i += 32) ifr[i] = T.ifree[i];
+        stage_peers_load(T, vbuf, threadIdx.x, 32);
         __syncwarp();
         if (threadIdx.x == 0) {
             sS.pstep = vbuf; sS.pmin = vbuf + MAXP; sS.pmax = vbuf + 2 * MAXP; sS.params0 = vbuf + 3 * MAXP;
             if (T.prior) { sS.prior = vbuf + 4 * MAXP; sS.priorlow = vbuf + 5 * MAXP; sS.priorup = vbuf + 6 * MAXP; }
             sS.ifree = ifr;
+            stage_peers_point(sS, vbuf);
         }
     }
     __syncthreads();

@@ -367,7 +367,7 @@ struct MomentFix {
 #define MC3B_FOLD_MINB 4
 #endif
 #ifndef MC3B_MOM_ACC
-#define MC3B_MOM_ACC 2
+#define MC3B_MOM_ACC 1
 #endif
 template <bool PRE, bool MOM>
 __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqArgs<double> a) {

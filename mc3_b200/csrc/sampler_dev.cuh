@@ -49,7 +49,30 @@ __device__ __forceinline__ void flags_wait(const mc3b_sampler_t& S, int64_t gen)
 // indices) staged in shared memory by the whole CTA in one round of loads, and the
 // sampler description repointed to them: a thread per chain otherwise pays a
 // chain of dependent L2 latencies per parameter.  buf: STAGE_DOUBLES doubles.
-constexpr int STAGE_DOUBLES = 7 * MAXP + MAXP / 2;
+// The peer pointer tables (X_peers, Z_peers, F_peers: [world] pointers in global memory)
+// are staged too: the Metropolis step stores nfree values into every device, and a
+// table read from global memory inside those loops cost one L2 round trip per (value,
+// peer) -- +3.3 us per peer and generation at config 2 (profiles/r2_bench_n*.json).
+constexpr int MAXW = 16;            // devices whose peer pointers are staged (more: read from global)
+constexpr int STAGE_PEERS = 7 * MAXP + MAXP / 2;       // offset of the pointer slots in the staging buffer
+constexpr int STAGE_DOUBLES = STAGE_PEERS + 3 * MAXW;
+__device__ __forceinline__ void stage_peers_load(const mc3b_sampler_t& T, double* buf, int tid, int nthreads) {
+    if (T.X_peers == nullptr || T.world > MAXW) return;
+    void** slot = reinterpret_cast<void**>(buf + STAGE_PEERS);
+    for (int i = tid; i < 3 * T.world; i += nthreads) {
+        const int v = i / T.world, p = i - v * T.world;
+        if (v == 0) slot[p] = T.X_peers[p];
+        else if (v == 1) { if (T.Z_peers) slot[MAXW + p] = T.Z_peers[p]; }
+        else if (T.F_peers) slot[2 * MAXW + p] = T.F_peers[p];
+    }
+}
+__device__ __forceinline__ void stage_peers_point(mc3b_sampler_t& S, double* buf) {
+    if (S.X_peers == nullptr || S.world > MAXW) return;
+    void** slot = reinterpret_cast<void**>(buf + STAGE_PEERS);
+    S.X_peers = reinterpret_cast<double* const*>(slot);
+    if (S.Z_peers) S.Z_peers = reinterpret_cast<double* const*>(slot + MAXW);
+    if (S.F_peers) S.F_peers = reinterpret_cast<int64_t* const*>(slot + 2 * MAXW);
+}
 __device__ __forceinline__ void stage_vectors(mc3b_sampler_t& S, double* buf) {
     const int np = S.npars, nf = S.nfree;
     const double* src[7] = {S.pstep, S.pmin, S.pmax, S.params0, S.prior, S.priorlow, S.priorup};
@@ -59,10 +82,12 @@ __device__ __forceinline__ void stage_vectors(mc3b_sampler_t& S, double* buf) {
     }
     int32_t* ifr = reinterpret_cast<int32_t*>(buf + 7 * MAXP);
     for (int i = threadIdx.x; i < nf; i += blockDim.x) ifr[i] = S.ifree[i];
+    stage_peers_load(S, buf, threadIdx.x, blockDim.x);
     __syncthreads();
     S.pstep = buf; S.pmin = buf + MAXP; S.pmax = buf + 2 * MAXP; S.params0 = buf + 3 * MAXP;
     if (S.prior) { S.prior = buf + 4 * MAXP; S.priorlow = buf + 5 * MAXP; S.priorup = buf + 6 * MAXP; }
     S.ifree = ifr;
+    stage_peers_point(S, buf);
 }
 
 // The random numbers chain c consumes in generation gen (chain.py:185, 197-203,
