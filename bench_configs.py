@@ -329,10 +329,17 @@ def config5(args):
         c = pop.counters()
         if roof is None:
             P = pop.nextp[pop.chain0:pop.chain0 + pop.nlocal]
-            kms, _ = timed(torch, lambda: pop._data_chisq_local(P), reps=5, warm=1)
+            moment = bool(getattr(pop, 'use_moment', False))
+            fuse = (pop.chain0, pop.gen, -1, False) if moment else None    # as the generation launches it
+            kms, _ = timed(torch, lambda: pop._data_chisq_local(P, fuse=fuse), reps=5, warm=1)
             peak = fp64_peak(torch, _lib)
             flops = float(w['flops_per_point'])*pop.nlocal*pop.ndata
-            roof = {'bound': 'fp64', 'kernel': 'k_sinegrid<USIG=true>' if pop.usig and pop.grid else 'k_model_chisq',
+            kname = 'k_model_chisq'
+            if pop.grid:
+                kname = ('k_fold_consts + k_sinefold<MOM> + Metropolis epilogue' if moment else
+                         'k_fold_consts + k_sinefold' if getattr(pop, 'd_fold', None) is not None else
+                         'k_sinegrid<USIG=%s>' % ('true' if pop.usig else 'false'))
+            roof = {'bound': 'fp64', 'kernel': kname,
                     'achieved': flops/(kms*1e-3)/1e12, 'peak': peak/1e12, 'unit': 'TFLOP/s',
                     'frac': flops/(kms*1e-3)/peak, 'ms_per_launch': kms,
                     'chains_per_launch': pop.nlocal, 'points_per_launch': pop.ndata,
