@@ -112,7 +112,14 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
  *                chain by a small kernel launched first, instead of by each of the nsplit
  *                CTAs of a chain group.  NULL: every CTA derives them (same bits).
  * moment         non-NULL (with uniform_sigma, fuse and work; fp64, MC3B_MODEL_SINUSOID_GRID):
- *                the sufficient-statistics form described at mc3b_moment_t below. */
+ *                the sufficient-statistics form described at mc3b_moment_t below.
+ * tile_x, dx, ntiles   (with folded or moment) PIECEWISE-uniform abscissa, e.g. a time series
+ *                of constant cadence with gaps: the caller has reordered x and data so that
+ *                entries [128 t, 128 t + 128) are the t-th run of 128 points spaced dx apart
+ *                starting at tile_x[t] (device array, ntiles entries; the tiles need not be
+ *                adjacent or ordered), followed by the n - 128 ntiles points that fill no
+ *                tile, which are evaluated one by one.  tile_x = NULL: one uniform grid from
+ *                x[0] to x[n-1].  mc3b_model_chisq_splits does not describe this layout. */
 struct mc3b_sampler;
 typedef struct mc3b_chisq_opts {
     int64_t plan_chains;
@@ -124,6 +131,9 @@ typedef struct mc3b_chisq_opts {
     const void* folded;
     void* work;
     const struct mc3b_moment* moment;
+    const double* tile_x;
+    double dx;
+    int64_t ntiles;
 } mc3b_chisq_opts_t;
 #define MC3B_FOLD_WORK 25
 
@@ -143,22 +153,26 @@ typedef struct mc3b_chisq_opts {
  *   folded  [n]  from mc3b_moment_prepare     tiles  [4 * (n/128)]  likewise
  *   c0ref, slref   the reference line (any; a least-squares line through the data keeps amp small)
  *   d2tot   sum of d'^2 over the n points     amp_max  e.g. 4000 (error < 1.2e-11)
+ *   xlo, xhi  smallest and largest abscissa (they bound |L'|)
  *   guard_hits  device int32 counter or NULL */
 typedef struct mc3b_moment {
     const double* folded;
     const double* tiles;
     double c0ref, slref, d2tot, amp_max;
+    double xlo, xhi;
     int32_t* guard_hits;
 } mc3b_moment_t;
 
-/* Chain-independent preparation for mc3b_moment_t: x_i = x0 + i dx.  Per 16-point
+/* Chain-independent preparation for mc3b_moment_t over `ntiles` whole tiles of 128
+ * points: x_i = x0 + i dx, or, with tile_x != NULL, tile_x[t] + j dx for point j of
+ * tile t (piecewise-uniform abscissa, see mc3b_chisq_opts_t).  Per 16-point
  * block, pair p joins points 7-p and 8+p: folded[16 b + 2 p] = -(d'_hi + d'_lo),
  * folded[16 b + 2 p + 1] = -(d'_hi - d'_lo); per 128-point tile t,
  * tiles[4 t ..] = {-2 sum e, -2 (16 sum_b (b - 3.5) sum_p e + sum (p + 1/2) o), sum e^2 + o^2, 0}
- * with e, o the half sum and half difference of a pair.  Only whole tiles are written. */
-int mc3b_moment_prepare(const double* data, int64_t n, double x0, double dx,
-                        double c0ref, double slref, double* folded, double* tiles,
-                        void* stream);
+ * with e, o the half sum and half difference of a pair. */
+int mc3b_moment_prepare(const double* data, int64_t ntiles, double x0, double dx,
+                        const double* tile_x, double c0ref, double slref,
+                        double* folded, double* tiles, void* stream);
 
 /* Chain-independent preparation for `folded` above: per block of 16 points, pair
  * p = 0..7 joins points 7-p and 8+p of the block;

@@ -45,7 +45,8 @@ class SamplerStruct(ctypes.Structure):
 class MomentStruct(ctypes.Structure):
     """mc3b_moment_t."""
     _fields_ = [('folded', c_vp), ('tiles', c_vp), ('c0ref', c_dbl), ('slref', c_dbl),
-                ('d2tot', c_dbl), ('amp_max', c_dbl), ('guard_hits', c_vp)]
+                ('d2tot', c_dbl), ('amp_max', c_dbl), ('xlo', c_dbl), ('xhi', c_dbl),
+                ('guard_hits', c_vp)]
 
 
 class ChisqOpts(ctypes.Structure):
@@ -53,7 +54,8 @@ class ChisqOpts(ctypes.Structure):
     _fields_ = [('plan_chains', c_i64), ('uniform_sigma', c_i32), ('advance', c_i32),
                 ('fuse', ctypes.POINTER(SamplerStruct)), ('fuse_done', c_vp),
                 ('c_off', c_i64), ('gen', c_i64), ('zrow0', c_i64), ('folded', c_vp), ('work', c_vp),
-                ('moment', ctypes.POINTER(MomentStruct))]
+                ('moment', ctypes.POINTER(MomentStruct)), ('tile_x', c_vp), ('dx', c_dbl),
+                ('ntiles', c_i64)]
 
 
 FOLD_WORK = 25                    # MC3B_FOLD_WORK
@@ -79,7 +81,7 @@ _SIGS = {
                                     c_vp, c_vp, c_i64, c_vp, c_i64, c_int,
                                     ctypes.POINTER(ChisqOpts), c_vp]),
     'mc3b_fold_data': (c_int, [c_vp, c_i64, c_vp, c_vp]),
-    'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),
     'mc3b_chisq_finish': (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,

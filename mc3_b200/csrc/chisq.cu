@@ -284,7 +284,8 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
                   int nsplit, int dtype, const mc3b_chisq_opts_t& o, cudaStream_t st) {
     ChisqArgs<T> A;
     A.params = params; A.ldp = ldp; A.nchains = nchains;
-    A.x = (const T*)x; A.d = (const T*)d; A.w = (const T*)w; A.fold = (const T*)o.folded; A.consts = nullptr; A.ldc = 0; A.consts_wait = 0; A.m = MomentArgs{}; A.n = n; A.partial = partial; A.ldpartial = ldpartial;
+    A.x = (const T*)x; A.d = (const T*)d; A.w = (const T*)w; A.fold = (const T*)o.folded; A.consts = nullptr; A.ldc = 0; A.consts_wait = 0; A.m = MomentArgs{}; A.n = n;
+    A.xt = nullptr; A.dxg = 0.0; A.ntiles = 0; A.partial = partial; A.ldpartial = ldpartial;
     const bool usig = o.uniform_sigma != 0;
     A.use_tma = ((((uintptr_t)x | (uintptr_t)d | (usig ? 0 : (uintptr_t)w)) & 15) == 0) ? 1 : 0;
     const int64_t plan_chains = o.plan_chains > 0 ? o.plan_chains : nchains;
@@ -311,6 +312,11 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
     if (model_id == MC3B_MODEL_SINUSOID_GRID) {
         if constexpr (std::is_same<T, double>::value) {
             if (sh.lc == 32 && A.use_tma && n >= 2) {
+                if (o.tile_x != nullptr) {
+                    MC3B_CHECK_ARG(usig && (o.folded || o.moment) && o.dx != 0.0 && o.ntiles >= 0 && o.ntiles * 128 <= n,
+                                   "tile_x needs uniform_sigma, folded or moment data, dx and ntiles <= n/128");
+                    A.xt = o.tile_x; A.dxg = o.dx; A.ntiles = o.ntiles;
+                }
                 if (usig && o.moment != nullptr) {
                     MC3B_CHECK_ARG(A.f.on && o.work, "the moment form runs fused with the Metropolis step (fuse, work)");
                     MC3B_CHECK_ARG(o.moment->folded && o.moment->tiles && o.moment->amp_max > 0.0 &&
@@ -319,6 +325,7 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
                     A.m.folded = o.moment->folded; A.m.tiles = o.moment->tiles;
                     A.m.c0ref = o.moment->c0ref; A.m.slref = o.moment->slref; A.m.d2tot = o.moment->d2tot;
                     A.m.amp_max = o.moment->amp_max; A.m.guard_hits = o.moment->guard_hits;
+                    A.m.xlo = o.moment->xlo; A.m.xhi = o.moment->xhi;
                     return mc3b_launch_sinefold(A, (double*)o.work, (unsigned)groups, (unsigned)nsplit, st);
                 }
                 if (usig && A.fold != nullptr && ((uintptr_t)A.fold & 15) == 0)
@@ -458,11 +465,11 @@ extern "C" int mc3b_fold_data(const double* data, int64_t n, double* out, void* 
     return mc3b_launch_fold(data, n, out, (cudaStream_t)stream);
 }
 
-extern "C" int mc3b_moment_prepare(const double* data, int64_t n, double x0, double dx, double c0ref, double slref,
-                                   double* folded, double* tiles, void* stream) {
-    MC3B_CHECK_ARG(data && folded && tiles && n > 0, "bad moment_prepare arguments");
+extern "C" int mc3b_moment_prepare(const double* data, int64_t ntiles, double x0, double dx, const double* tile_x,
+                                   double c0ref, double slref, double* folded, double* tiles, void* stream) {
+    MC3B_CHECK_ARG(data && folded && tiles && ntiles >= 0, "bad moment_prepare arguments");
     MC3B_CHECK_ARG((((uintptr_t)tiles) & 31) == 0, "tiles must be 32-byte aligned");
-    return mc3b_launch_moment_prepare(data, n, x0, dx, c0ref, slref, folded, tiles, (cudaStream_t)stream);
+    return mc3b_launch_moment_prepare(data, ntiles, x0, dx, tile_x, c0ref, slref, folded, tiles, (cudaStream_t)stream);
 }
 
 extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,

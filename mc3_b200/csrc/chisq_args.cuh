@@ -50,6 +50,7 @@ struct MomentArgs {
     const double* folded;           // nullptr: not the moment form
     const double* tiles;
     double c0ref, slref, d2tot, amp_max;
+    double xlo, xhi;                // range of the abscissa (bound of the line term of the guard)
     int32_t* guard_hits;
 };
 
@@ -60,6 +61,12 @@ template <typename T> struct ChisqArgs {
     int64_t ldp, nchains;
     const T *x, *d, *w;
     const T* fold;                  // mirrored-pair copy of d (mc3b_fold_data) or nullptr
+    // k_sinefold on a piecewise-uniform abscissa (include/mc3b200.h, tile_x): origin of every whole
+    // 128-point tile, the common step, the number of whole tiles; x/d hold the tiles first, then
+    // the points that fill no tile.  nullptr: one uniform grid, x_i = x[0] + i (x[n-1] - x[0])/(n-1)
+    const double* xt;
+    double dxg;
+    int64_t ntiles;
     const double* consts;           // k_sinefold: per-chain constants [NCONST, ldc] (k_fold_consts) or nullptr
     int64_t ldc;
     int consts_wait;                // launched as a programmatic dependent of k_fold_consts
@@ -172,5 +179,5 @@ using namespace mc3b_chisq;
 int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_sinefold(const ChisqArgs<double>& a, double* work, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st);
-int mc3b_launch_moment_prepare(const double* d, int64_t n, double x0, double dx, double c0ref, double slref,
-                               double* folded, double* tiles, cudaStream_t st);
+int mc3b_launch_moment_prepare(const double* d, int64_t ntiles, double x0, double dx, const double* tile_x,
+                               double c0ref, double slref, double* folded, double* tiles, cudaStream_t st);

@@ -267,14 +267,13 @@ __device__ __forceinline__ void derive(double period, double dx, Consts& K) {
 }  // namespace fold
 
 __global__ void __launch_bounds__(128) k_fold_consts(const double* __restrict__ params, int64_t ldp, int64_t nchains,
-                                                     const double* __restrict__ x, int64_t n, double* __restrict__ out,
-                                                     int64_t ld) {
+                                                     const double* __restrict__ x, int64_t n, double dxg,
+                                                     double* __restrict__ out, int64_t ld) {
     asm volatile("griddepcontrol.launch_dependents;");
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= nchains) return;
     using fold::NP;
-    const double x0 = x[0];
-    const double dx = (x[n - 1] - x0) / (double)(n - 1);
+    const double dx = dxg != 0.0 ? dxg : (x[n - 1] - x[0]) / (double)(n - 1);
     fold::Consts K;
     fold::derive(params[c * ldp + 1], dx, K);
     double* o = out + c;
@@ -317,12 +316,11 @@ struct MomentFix {
         bool bad = false;
         const double* p = a.params + cl * a.ldp;
         if (act) {
-            const double n = (double)a.n, x0 = a.x[0];
-            const double dx = (a.x[a.n - 1] - x0) / (n - 1.0);
+            // |L'| <= sqrt(n) max(|L'(xlo)|, |L'(xhi)|): a line is extremal at the ends of its range
+            const double n = (double)a.n;
             const double c0 = p[3] - m.c0ref, sl = p[4] - m.slref;
-            const double lm = fma(sl, fma(0.5 * (n - 1.0), dx, x0), c0), g = sl * dx;
-            const double l2 = n * (lm * lm + g * g * (n * n - 1.0) * (1.0 / 12.0));
-            const double mag = fabs(p[0]) * sqrt(n) + sqrt(l2) + sqrt(m.d2tot);
+            const double lmax = fmax(fabs(fma(sl, m.xlo, c0)), fabs(fma(sl, m.xhi, c0)));
+            const double mag = (fabs(p[0]) + lmax) * sqrt(n) + sqrt(m.d2tot);
             bad = !(mag * mag * (w0 * w0) <= m.amp_max * nxt);        // NaN: exact path too
         }
         if (!__syncthreads_or(bad)) return;
@@ -384,10 +382,14 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     const bool live = c < a.nchains;
     if (!live) c = a.nchains - 1;
 
-    const int64_t nfull = a.n / TILE;
+    // piecewise-uniform abscissa: the plan was made for n / TILE tiles, a few of which may not exist
+    const bool seg = a.xt != nullptr;
+    const int64_t nfull = seg ? a.ntiles : a.n / TILE;
     int64_t tb, te;
     if (a.nsched > 0) { tb = a.tstart[blockIdx.y]; te = a.tstart[blockIdx.y + 1]; }
-    else { tb = nfull * blockIdx.y / gridDim.y; te = nfull * (blockIdx.y + 1) / gridDim.y; }
+    else { tb = (a.n / TILE) * blockIdx.y / gridDim.y; te = (a.n / TILE) * (blockIdx.y + 1) / gridDim.y; }
+    if (tb > nfull) tb = nfull;
+    if (te > nfull) te = nfull;
     const int64_t nt = te - tb;
 
     if (threadIdx.x == 0) {
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
         for (int s = 0; s < NSTAGE && s < nt; s++) issue(tb + s, s);
 
     const double x0 = a.x[0];
-    const double dx = (a.x[a.n - 1] - x0) / (double)(a.n - 1);
+    const double dx = seg ? a.dxg : (a.x[a.n - 1] - x0) / (double)(a.n - 1);
     const double* p = a.params + c * a.ldp;
     const double amp = p[0], ph = p[2], c0 = p[3], sl = p[4];
     // MOM: the line relative to the reference line the data were centred on
@@ -444,12 +446,13 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
         const int st = (int)(it % NSTAGE);
         const uint32_t par = (uint32_t)((it / NSTAGE) & 1);
         const int tr = (int)(it % RESTART);
-        // centre of the tile's first block: x0 + (first point + 7.5) dx, one rounding
-        const double xc = fma((double)((tb + it) * TILE) + 7.5, dx, x0);
-        if (tr == 0) {
+        // centre of the tile's first block: x0 + (first point + 7.5) dx, one rounding; on a
+        // piecewise-uniform abscissa every tile has its own origin and its own anchor
+        const double xc = seg ? fma(7.5, dx, a.xt[tb + it]) : fma((double)((tb + it) * TILE) + 7.5, dx, x0);
+        if (tr == 0 || seg) {
             const double th = fma(xc, k, ph);
             key = max(keybase, max(sin_arg_key(th), sin_arg_key(fma((double)(RESTART * TILE), dth, th))));
-            if (rcount == 0) {
+            if (rcount == 0 || seg) {
                 fast_sincos_core(th, S0, C0);
                 S0 *= amp; C0 *= amp;
             } else {
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
             }
         } else {                                    // guarded chains: library sine per point, raw data
             double qd = 0.0;
-            const double xt = fma((double)((tb + it) * TILE), dx, x0);
+            const double xt = seg ? a.xt[tb + it] : fma((double)((tb + it) * TILE), dx, x0);
             const double* dt = a.d + (tb + it) * TILE;
             for (int i = 0; i < TILE; i++) {
                 const double r = direct(fma((double)i, dx, xt)) - dt[i];
@@ -529,7 +532,16 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     }
 
     acc *= 2.0;
-    if (blockIdx.y == gridDim.y - 1) {              // ragged tail, straight from global memory
+    if (seg) {                                      // points that fill no tile: shared out over the splits
+        const int64_t nl = a.n - nfull * TILE;
+        const int64_t lb = nfull * TILE + nl * blockIdx.y / gridDim.y, le = nfull * TILE + nl * (blockIdx.y + 1) / gridDim.y;
+        double t = 0.0;
+        for (int64_t i = lb; i < le; i++) {
+            const double r = direct(a.x[i]) - a.d[i];
+            t = fma(r, r, t);
+        }
+        acc += t;
+    } else if (blockIdx.y == gridDim.y - 1) {       // ragged tail, straight from global memory
         double t = 0.0;
         for (int64_t i = nfull * TILE; i < a.n; i++) {
             const double r = direct(a.x[i]) - a.d[i];
@@ -560,18 +572,19 @@ __global__ void k_fold(const double* __restrict__ d, int64_t nblk16, double* __r
 // half difference of a pair); tiles[t] = {-2 sum e, -2 (16 sum_b (b - 3.5) E1_b + sum dl o),
 // sum e^2 + o^2, 0}.  Fixed-order shuffles: same bits on every run.
 __global__ void __launch_bounds__(128) k_moment_prepare(const double* __restrict__ d, int64_t ntiles, double x0, double dx,
-                                                        double c0ref, double slref, double* __restrict__ folded,
-                                                        double* __restrict__ tiles) {
+                                                        const double* __restrict__ tile_x, double c0ref, double slref,
+                                                        double* __restrict__ folded, double* __restrict__ tiles) {
     const int64_t t = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= ntiles) return;
     const int lane = threadIdx.x & 31, b = lane >> 2;
+    const double xo = tile_x ? tile_x[t] : fma((double)(t * 128), dx, x0);      // abscissa of the tile's first point
     double m0 = 0.0, m1 = 0.0, m2 = 0.0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
         const int pp = 2 * (lane & 3) + h;
         const int64_t ilo = t * 128 + b * 16 + 7 - pp, ihi = t * 128 + b * 16 + 8 + pp;
-        const double lo = d[ilo] - fma(slref, fma((double)ilo, dx, x0), c0ref);
-        const double hi = d[ihi] - fma(slref, fma((double)ihi, dx, x0), c0ref);
+        const double lo = d[ilo] - fma(slref, fma((double)(b * 16 + 7 - pp), dx, xo), c0ref);
+        const double hi = d[ihi] - fma(slref, fma((double)(b * 16 + 8 + pp), dx, xo), c0ref);
         const double e = 0.5 * (hi + lo), o = 0.5 * (hi - lo);
         folded[t * 128 + b * 16 + 2 * pp] = -2.0 * e;
         folded[t * 128 + b * 16 + 2 * pp + 1] = -2.0 * o;
@@ -602,7 +615,8 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
     }
     ChisqArgs<double> a = a0;
     a.consts = work; a.ldc = a.nchains; a.consts_wait = 0;
-    k_fold_consts<<<(unsigned)((a.nchains + 127) / 128), 128, 0, st>>>(a.params, a.ldp, a.nchains, a.x, a.n, work, a.ldc);
+    k_fold_consts<<<(unsigned)((a.nchains + 127) / 128), 128, 0, st>>>(a.params, a.ldp, a.nchains, a.x, a.n,
+                                                                        a.xt ? a.dxg : 0.0, work, a.ldc);
     MC3B_CHECK_LAUNCH("k_fold_consts");
     static const bool pdl = !(getenv("MC3B_FOLD_PDL") && atoi(getenv("MC3B_FOLD_PDL")) == 0);
     if (pdl) {
@@ -626,11 +640,10 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
     return MC3B_OK;
 }
 
-int mc3b_launch_moment_prepare(const double* d, int64_t n, double x0, double dx, double c0ref, double slref,
-                               double* folded, double* tiles, cudaStream_t st) {
-    const int64_t nt = n / 128;
+int mc3b_launch_moment_prepare(const double* d, int64_t nt, double x0, double dx, const double* tile_x, double c0ref,
+                               double slref, double* folded, double* tiles, cudaStream_t st) {
     if (nt == 0) return MC3B_OK;
-    k_moment_prepare<<<(unsigned)((nt + 3) / 4), 128, 0, st>>>(d, nt, x0, dx, c0ref, slref, folded, tiles);
+    k_moment_prepare<<<(unsigned)((nt + 3) / 4), 128, 0, st>>>(d, nt, x0, dx, tile_x, c0ref, slref, folded, tiles);
     MC3B_CHECK_LAUNCH("k_moment_prepare");
     return MC3B_OK;
 }

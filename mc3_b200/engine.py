@@ -35,6 +35,7 @@ import torch
 
 from . import _lib
 from .models import BuiltinModel, TorchModel, SINUSOID, SINUSOID_GRID
+from . import gridseg
 from .parallel import chain_slice, allgather_rows, gather_history, sum_owned
 
 
@@ -177,20 +178,36 @@ class Population:
             # kernel (models.cuh SineGridModel); MC3B_NO_GRID=1 forces the plain one.
             self.chisq_model_id = func.model_id
             self.grid = False
+            self.seg = None                    # piecewise-uniform layout (gridseg.tile_layout) or None
+            kx, kd = self.d_x, self.d_data     # what the model kernels read
+            nfold = self.ndata                 # leading entries of kd that form whole tiles
+            fold_ok = self.usig and not os.environ.get('MC3B_NO_FOLD')
             if func.model_id == SINUSOID and self.dtype == _lib.F64 and x.size >= 8 \
                     and not os.environ.get('MC3B_NO_GRID'):
                 ideal = x[0] + np.arange(x.size)*((x[-1] - x[0])/(x.size - 1))
                 if x[-1] != x[0] and np.max(np.abs(x - ideal)) <= 8*np.finfo(float).eps*np.max(np.abs(x)):
                     self.chisq_model_id = SINUSOID_GRID
                     self.grid = True
+                elif fold_ok and not os.environ.get('MC3B_NO_SEG'):
+                    # constant cadence with gaps: whole 128-point tiles first, the points
+                    # that fill no tile last (include/mc3b200.h, tile_x)
+                    self.seg = gridseg.tile_layout(x)
+                    if self.seg is not None:
+                        self.chisq_model_id = SINUSOID_GRID
+                        self.grid = True
+                        with torch.cuda.device(self.dev):
+                            perm = torch.from_numpy(self.seg['perm']).to(self.dev)
+                            kx, kd = self.d_x[perm].contiguous(), self.d_data[perm].contiguous()
+                            self.d_tile_x = torch.from_numpy(np.ascontiguousarray(x[self.seg['starts']])).to(self.dev)
+                        nfold = 128*self.seg['starts'].size
             # with one uncertainty for all points the grid kernel works on point pairs
             # mirrored about block centres (csrc/chisq_grid.cu k_sinefold): the paired
             # copy of the data is prepared once here.  MC3B_NO_FOLD=1 disables.
             self.d_fold = None
-            if self.grid and self.usig and not os.environ.get('MC3B_NO_FOLD'):
+            if self.grid and fold_ok:
                 with torch.cuda.device(self.dev):
-                    self.d_fold = torch.empty_like(self.d_data)
-                    _lib.call('mc3b_fold_data', self.d_data.data_ptr(), self.ndata,
+                    self.d_fold = torch.zeros_like(kd)
+                    _lib.call('mc3b_fold_data', kd.data_ptr(), nfold,
                               self.d_fold.data_ptr(), _lib.stream_ptr())
             # ... and, inside the generation loop, on sufficient statistics of those pairs
             # (k_sinefold<MOM>, one multiply-add per point; include/mc3b200.h mc3b_moment_t):
@@ -201,7 +218,7 @@ class Population:
             # MC3B_NO_MOMENT=1 disables.
             self.moment = None
             self.use_moment = False
-            if self.d_fold is not None and self.shard == 'chains' and x.size >= 256 \
+            if self.d_fold is not None and self.shard == 'chains' and nfold >= 256 \
                     and not os.environ.get('MC3B_NO_MOMENT') and not os.environ.get('MC3B_NO_FUSE'):
                 with torch.cuda.device(self.dev):
                     # least-squares line through the data and the sum of squares about it,
@@ -212,16 +229,18 @@ class Population:
                     c0r_t = dm - slr_t*xm
                     res = self.d_data - (c0r_t + slr_t*self.d_x)
                     c0r, slr, d2tot = (float(v) for v in torch.stack([c0r_t, slr_t, torch.dot(res, res)]).cpu())
-                    self.d_mfold = torch.zeros_like(self.d_data)
-                    self.d_mtiles = torch.zeros((x.size//128, 4), **f64)
+                    self.d_mfold = torch.zeros_like(kd)
+                    self.d_mtiles = torch.zeros((max(nfold//128, 1), 4), **f64)
                     self.guard_hits = torch.zeros(1, dtype=torch.int32, device=self.dev)
-                    _lib.call('mc3b_moment_prepare', self.d_data.data_ptr(), self.ndata, float(x[0]),
-                              float((x[-1] - x[0])/(x.size - 1)), c0r, slr,
+                    dxg = self.seg['dx'] if self.seg else float((x[-1] - x[0])/(x.size - 1))
+                    _lib.call('mc3b_moment_prepare', kd.data_ptr(), nfold//128, float(x[0]), dxg,
+                              self.d_tile_x.data_ptr() if self.seg else None, c0r, slr,
                               self.d_mfold.data_ptr(), self.d_mtiles.data_ptr(), _lib.stream_ptr())
                 M = _lib.MomentStruct()
                 M.folded, M.tiles = self.d_mfold.data_ptr(), self.d_mtiles.data_ptr()
                 M.c0ref, M.slref, M.d2tot = c0r, slr, d2tot
                 M.amp_max = float(os.environ.get('MC3B_MOMENT_AMP', 4000.0))
+                M.xlo, M.xhi = float(x.min()), float(x.max())
                 M.guard_hits = self.guard_hits.data_ptr()
                 self.moment = M
                 self.use_moment = True
@@ -234,7 +253,7 @@ class Population:
                 self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
                                                 (self.d_x, self.d_data, self.d_invsig))
             else:
-                self.k_x, self.k_d, self.k_w = self.d_x, self.d_data, self.d_invsig
+                self.k_x, self.k_d, self.k_w = kx, kd, self.d_invsig
         elif self.shard == 'data':
             raise ValueError("shard='data' needs a built-in model")
         elif isinstance(func, TorchModel):
@@ -477,6 +496,9 @@ class Population:
             o = _lib.ChisqOpts()
             o.plan_chains = self._plan_chains(nb) if self.plan_chains else 0
             o.uniform_sigma = 1 if self.usig else 0
+            if self.seg is not None:
+                o.tile_x, o.dx = self.d_tile_x.data_ptr(), self.seg['dx']
+                o.ntiles = self.seg['starts'].size
             if self.d_fold is not None:
                 o.folded = self.d_fold.data_ptr()
                 if not os.environ.get('MC3B_NO_FOLD_CONSTS') or (fuse is not None and self.use_moment):

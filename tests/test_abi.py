@@ -121,7 +121,7 @@ def test_chisq_opts_layout_matches_header():
                 names.append(re.findall(r'[A-Za-z_0-9]+', part)[-1])
     assert names == [f[0] for f in _lib.ChisqOpts._fields_]
     import ctypes
-    assert ctypes.sizeof(_lib.ChisqOpts) == 80
+    assert ctypes.sizeof(_lib.ChisqOpts) == 104
 
 
 def test_plan_is_a_function_of_plan_chains_only():

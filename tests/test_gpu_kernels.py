@@ -657,3 +657,29 @@ def test_population_uses_the_folded_kernel_for_one_uncertainty(mc3, monkeypatch)
     unc[5] *= 1.5
     pop3 = Population(w['data'], unc, mc3.models.sinusoid, w['params'], [w['x']], {}, **kw)
     assert pop3.grid and not pop3.usig and pop3.d_fold is None
+
+
+def test_config4_full_size_properties(mc3):
+    """BASELINE config 4 at its stated size (1e8 points): time_avg (1000 bin sizes) and
+    bin_array against direct numpy sums on a sample of bin sizes -- size-independent
+    properties, since the oracle's O(N x sizes) loop does not finish in seconds here."""
+    n = 100_000_000
+    rs = np.random.RandomState(44)
+    d = rs.standard_normal(n)
+    d += 0.05*np.sin(np.arange(n)*1e-4)                   # a little red noise
+    rms, lo, hi, err, bsz = mc3.stats.time_avg(d, 1000, 1)
+    assert len(rms) == len(bsz) and np.all(np.diff(bsz) >= 0)
+    sd = np.std(d)
+    for i in (0, 1, 57, len(rms)//2, len(rms) - 2, len(rms) - 1):
+        b = int(bsz[i])
+        M = n//b
+        means = d[:M*b].reshape(M, b).mean(axis=1)
+        np.testing.assert_allclose(rms[i], np.sqrt(np.mean(means**2)), rtol=R64)
+        np.testing.assert_allclose(err[i], sd*np.sqrt(M/(b*(M - 1.0))), rtol=R64)
+    b = mc3.stats.bin_array(d, 100)
+    np.testing.assert_allclose(b, d.reshape(-1, 100).mean(axis=1), rtol=1e-12, atol=1e-15)
+    u = 0.5 + np.abs(d)
+    bw, bs = mc3.stats.bin_array(d, 100, u)
+    w = 1.0/u.reshape(-1, 100)**2
+    np.testing.assert_allclose(bs, np.sqrt(1.0/w.sum(axis=1)), rtol=1e-12)
+    np.testing.assert_allclose(bw, (d.reshape(-1, 100)*w).sum(axis=1)/w.sum(axis=1), rtol=1e-11, atol=1e-14)

@@ -39,8 +39,15 @@ def test_moment_prepare_matches_numpy(mc3):
         dd = torch.from_numpy(d).to(dev)
         df = torch.full((n,), 7.0, dtype=torch.float64, device=dev)
         dt = torch.zeros((n//128, 4), dtype=torch.float64, device=dev)
-        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n, x0, dx, c0r, slr, df.data_ptr(),
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, x0, dx, None, c0r, slr, df.data_ptr(),
                   dt.data_ptr(), _lib.stream_ptr())
+        # the same tiles addressed through their origins (piecewise-uniform layout)
+        tx = torch.from_numpy(x0 + 128*dx*np.arange(n//128)).to(dev)
+        df2, dt2 = torch.full_like(df, 7.0), torch.zeros_like(dt)
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, 0.0, dx, tx.data_ptr(), c0r, slr,
+                  df2.data_ptr(), dt2.data_ptr(), _lib.stream_ptr())
+        np.testing.assert_allclose(df2.cpu().numpy(), df.cpu().numpy(), rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(dt2.cpu().numpy(), dt.cpu().numpy(), rtol=1e-10, atol=1e-10)
         nt = n//128*128
         np.testing.assert_allclose(df.cpu().numpy()[:nt], f, rtol=1e-13, atol=1e-14)
         assert np.all(df.cpu().numpy()[nt:] == 7.0)
@@ -172,3 +179,91 @@ def test_moment_run_is_deterministic_and_graph_equals_eager(mc3):
         outs.append((pop.Z.cpu().numpy(), pop.log_post.cpu().numpy()))
     for o in outs[1:]:
         assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+# ---- piecewise-uniform abscissa: a constant cadence with gaps ----------------------
+def _gapped(n, seed):
+    rs = np.random.RandomState(seed)
+    x = np.linspace(0.0, 10.0, n)
+    keep = np.ones(n, dtype=bool)
+    for lo, w in ((n//5, n//33), (n//2, 10), (3*n//4, 1), (n - 700, 300)):
+        keep[lo:lo + w] = False
+    x = x[keep]
+    x[x > 6.0] += 0.37*(x[1] - x[0])                 # the cadence resumes off the original grid
+    return x, rs
+
+
+def test_pair_kernel_on_a_gapped_series_matches_oracle(mc3):
+    """k_sinefold with tile origins (opts.tile_x): whole tiles of the runs first, the
+    points that fill no tile shared out over the splits; against the per-point
+    evaluation and against the plain sinusoid kernel on the same arrays."""
+    from mc3_b200 import _lib, gridseg
+    dev = torch.device('cuda')
+    for n, nch in ((100000, 256), (20000, 160)):
+        x, rs = _gapped(n, n)
+        L = gridseg.tile_layout(x)
+        assert L is not None and L['nleft'] > 0 and L['starts'].size >= 10
+        truth = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+        sigma = 0.5
+        data = om.sinusoid(truth, x) + rs.normal(0, sigma, x.size)
+        P = truth*(1 + 0.02*rs.standard_normal((nch, 5)))
+        P[::9, 1] = rs.uniform(2.2, 12, P[::9].shape[0])*L['dx']
+        xp, dp = x[L['perm']], data[L['perm']]
+        dP, dx_, dd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (P, xp, dp))
+        dw = torch.tensor([1.0/sigma], dtype=torch.float64, device=dev)
+        tx = torch.from_numpy(np.ascontiguousarray(x[L['starts']])).to(dev)
+        nt = L['starts'].size
+        df = torch.zeros_like(dd)
+        _lib.call('mc3b_fold_data', dd.data_ptr(), 128*nt, df.data_ptr(), _lib.stream_ptr())
+        ns = ctypes.c_int(0)
+        _lib.call('mc3b_model_chisq_plan', nch, x.size, _lib.F64, ctypes.byref(ns))
+        outs = []
+        for work in (False, True):
+            o = _lib.ChisqOpts()
+            o.uniform_sigma = 1
+            o.folded, o.tile_x, o.dx, o.ntiles = df.data_ptr(), tx.data_ptr(), L['dx'], nt
+            if work:
+                wk = torch.empty((_lib.FOLD_WORK, nch), dtype=torch.float64, device=dev)
+                o.work = wk.data_ptr()
+            part = torch.empty((ns.value, nch), dtype=torch.float64, device=dev)
+            _lib.call('mc3b_model_chisq_ex', 4, _lib.F64, dP.data_ptr(), 5, nch, 5, dx_.data_ptr(),
+                      dd.data_ptr(), dw.data_ptr(), x.size, part.data_ptr(), nch, ns.value,
+                      ctypes.byref(o), _lib.stream_ptr())
+            outs.append(part.sum(dim=0).cpu().numpy())
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+        np.testing.assert_allclose(outs[0], want, rtol=R64)
+        assert np.array_equal(outs[0], outs[1])
+
+
+def test_population_on_a_gapped_series(mc3, monkeypatch):
+    """Population finds the piecewise-uniform layout, its chi-squared equals the oracle's
+    on the original arrays, and the run (moment form inside the loop) walks the same
+    chain as the plain sinusoid kernel (MC3B_NO_SEG=1)."""
+    from mc3_b200.engine import Population
+    x, rs = _gapped(40000, 8)
+    truth = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+    sigma = 0.5
+    data = om.sinusoid(truth, x) + rs.normal(0, sigma, x.size)
+    kw = dict(pstep=np.array([1e-2, 1e-3, 1e-2, 1e-2, 1e-3]), pmin=np.array([0.0, 1.0, -np.pi, 0.0, -1.0]),
+              pmax=np.array([5.0, 5.0, np.pi, 10.0, 1.0]), nchains=256, sampler='demc', fepsilon=0.01,
+              nzchain=20, seed=21)
+    runs = []
+    for env in (None, 'MC3B_NO_SEG'):
+        if env:
+            monkeypatch.setenv(env, '1')
+        pop = Population(data, np.full(x.size, sigma), mc3.models.sinusoid, truth*1.001, [x], {}, **kw)
+        assert (pop.seg is not None) == (env is None) and pop.grid == (env is None)
+        assert pop.use_moment == (env is None)
+        P = truth*(1 + 0.01*np.random.RandomState(1).standard_normal((128, 5)))
+        got = pop.chisq(torch.as_tensor(P, device=pop.dev)).cpu().numpy()
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+        np.testing.assert_allclose(got, want, rtol=R64)
+        pop.init_population('normal')
+        pop.run(20)
+        torch.cuda.synchronize()
+        runs.append((pop.zchain.cpu().numpy(), pop.log_post.cpu().numpy(), pop.Z.cpu().numpy()))
+        if env is None:
+            assert int(pop.guard_hits.item()) == 0
+    assert np.array_equal(runs[0][0], runs[1][0])
+    np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-10)
+    assert np.array_equal(runs[0][2], runs[1][2])

@@ -180,3 +180,32 @@ def test_summary_stats_text_matches_reference_golden(tmp_path):
     got = ms.summary_stats(post, out, filename=str(tmp_path/'s.txt'), device=False)
     assert got == open(tmp_path/'s.txt').read()
     assert got == want
+
+
+def test_tile_layout_of_piecewise_uniform_abscissae():
+    """mc3_b200/gridseg.py: runs of a constant cadence are cut into whole 128-point tiles;
+    what fills no tile is left over; anything else is refused."""
+    from mc3_b200.gridseg import tile_layout, TILE
+    x = np.linspace(0, 10, 100000)
+    L = tile_layout(x)
+    assert L['starts'].size == 100000//TILE and L['nleft'] == 100000 % TILE
+    keep = np.ones(x.size, bool)
+    keep[20000:23000] = False
+    keep[60000:60010] = False
+    keep[77777] = False
+    xg = x[keep]
+    xg[xg > 7.0] += 0.4*(x[1] - x[0])
+    L = tile_layout(xg)
+    assert L is not None and 0 < L['nleft'] <= 4*TILE
+    assert np.array_equal(np.sort(L['perm']), np.arange(xg.size))
+    assert abs(L['dx'] - (x[1] - x[0])) < 1e-15
+    nt = L['starts'].size
+    tiles = xg[L['perm'][:nt*TILE]].reshape(nt, TILE)
+    assert np.array_equal(tiles[:, 0], xg[L['starts']])
+    assert np.max(np.abs(tiles - (tiles[:, :1] + np.arange(TILE)*L['dx']))) <= 8*np.finfo(float).eps*10.4
+    assert tile_layout(x + 1e-9*np.sin(np.arange(x.size))) is None              # jitter
+    assert tile_layout(np.sort(np.random.RandomState(0).uniform(0, 10, 5000))) is None
+    assert tile_layout(x[::-1]) is None and tile_layout(x[:100]) is None
+    # many short runs: too much would be left over
+    short = np.concatenate([i*5.0 + np.arange(150)*0.01 for i in range(40)])
+    assert tile_layout(short) is None
