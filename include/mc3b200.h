@@ -113,8 +113,9 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
  *                CTAs of a chain group.  NULL: every CTA derives them (same bits).
  * moment         non-NULL (with uniform_sigma, fuse and work; fp64, MC3B_MODEL_SINUSOID_GRID):
  *                the sufficient-statistics form described at mc3b_moment_t below.
- * tile_x, dx, ntiles   (with folded or moment) PIECEWISE-uniform abscissa, e.g. a time series
+ * tile_x, dx, ntiles   (fp64, MC3B_MODEL_SINUSOID_GRID) PIECEWISE-uniform abscissa, e.g. a time series
  *                of constant cadence with gaps: the caller has reordered x and data so that
+ *                (and invsig, when it is per point) so that
  *                entries [128 t, 128 t + 128) are the t-th run of 128 points spaced dx apart
  *                starting at tile_x[t] (device array, ntiles entries; the tiles need not be
  *                adjacent or ordered), followed by the n - 128 ntiles points that fill no

@@ -313,8 +313,7 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
         if constexpr (std::is_same<T, double>::value) {
             if (sh.lc == 32 && A.use_tma && n >= 2) {
                 if (o.tile_x != nullptr) {
-                    MC3B_CHECK_ARG(usig && (o.folded || o.moment) && o.dx != 0.0 && o.ntiles >= 0 && o.ntiles * 128 <= n,
-                                   "tile_x needs uniform_sigma, folded or moment data, dx and ntiles <= n/128");
+                    MC3B_CHECK_ARG(o.dx != 0.0 && o.ntiles >= 0 && o.ntiles * 128 <= n, "tile_x needs dx and ntiles <= n/128");
                     A.xt = o.tile_x; A.dxg = o.dx; A.ntiles = o.ntiles;
                 }
                 if (usig && o.moment != nullptr) {

@@ -62,8 +62,11 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
     const bool live = c < a.nchains;
     if (!live) c = a.nchains - 1;                   // idle lanes shadow the last chain
 
+    // piecewise-uniform abscissa (tile origins a.xt, include/mc3b200.h tile_x): every tile is
+    // anchored on its own origin; the plan may hold a few tiles that do not exist
+    const bool seg = a.xt != nullptr;
     const double x0 = a.x[0];
-    const double dx = (a.x[a.n - 1] - x0) / (double)(a.n - 1);
+    const double dx = seg ? a.dxg : (a.x[a.n - 1] - x0) / (double)(a.n - 1);
     const double* p = a.params + c * a.ldp;
     const double amp = p[0], k = 6.283185307179586476925287 / p[1], ph = p[2], c0 = p[3], sl = p[4];
     const double dth = k * dx;
@@ -81,10 +84,12 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
                             ? MC3B_SIN_KEY_LIMIT : 0;
     auto direct = [&](double x) { return fma(amp, sin(fma(x, k, ph)), fma(sl, x, c0)); };
 
-    const int64_t nfull = a.n / TILE;
+    const int64_t nfull = seg ? a.ntiles : a.n / TILE;
     int64_t tb, te;
     if (a.nsched > 0) { tb = a.tstart[blockIdx.y]; te = a.tstart[blockIdx.y + 1]; }
-    else { tb = nfull * blockIdx.y / gridDim.y; te = nfull * (blockIdx.y + 1) / gridDim.y; }
+    else { tb = (a.n / TILE) * blockIdx.y / gridDim.y; te = (a.n / TILE) * (blockIdx.y + 1) / gridDim.y; }
+    if (tb > nfull) tb = nfull;
+    if (te > nfull) te = nfull;
     const int64_t nt = te - tb;
 
     if (threadIdx.x == 0) {
@@ -106,13 +111,13 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
     for (int64_t it = 0; it < nt; it++) {
         const int st = (int)(it % NSTAGE);
         const uint32_t par = (uint32_t)((it / NSTAGE) & 1);
-        const int tr = (int)(it % RESTART);             // tile within the restart interval
-        const double xt = fma((double)((tb + it) * TILE), dx, x0);
+        const int tr = seg ? 0 : (int)(it % RESTART);   // tile within the restart interval
+        const double xt = seg ? a.xt[tb + it] : fma((double)((tb + it) * TILE), dx, x0);
         if (tr == 0) {
             // ---- restart: anchors of the four sequences (no data needed yet) ----
             const double th = fma(xt, k, ph);
             key = max(keybase, max(sin_arg_key(th), sin_arg_key(fma((double)(RESTART * TILE), dth, th))));
-            if (rcount == 0) {
+            if (rcount == 0 || seg) {
                 fast_sincos_core(th, S0, C0);
                 S0 *= amp; C0 *= amp;
             } else {
@@ -205,7 +210,16 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
         }
     }
 
-    if (blockIdx.y == gridDim.y - 1) {              // ragged tail, straight from global memory
+    if (seg) {                                      // points that fill no tile: shared out over the splits
+        const int64_t nl = a.n - nfull * TILE;
+        const int64_t lb = nfull * TILE + nl * blockIdx.y / gridDim.y, le = nfull * TILE + nl * (blockIdx.y + 1) / gridDim.y;
+        double t = 0.0;
+        for (int64_t i = lb; i < le; i++) {
+            const double r = USIG ? direct(a.x[i]) - a.d[i] : (direct(a.x[i]) - a.d[i]) * a.w[i];
+            t = fma(r, r, t);
+        }
+        acc += t;
+    } else if (blockIdx.y == gridDim.y - 1) {       // ragged tail, straight from global memory
         double t = 0.0;
         for (int64_t i = nfull * TILE; i < a.n; i++) {
             const double r = USIG ? direct(a.x[i]) - a.d[i] : (direct(a.x[i]) - a.d[i]) * a.w[i];

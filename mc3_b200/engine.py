@@ -179,7 +179,7 @@ class Population:
             self.chisq_model_id = func.model_id
             self.grid = False
             self.seg = None                    # piecewise-uniform layout (gridseg.tile_layout) or None
-            kx, kd = self.d_x, self.d_data     # what the model kernels read
+            kx, kd, kw = self.d_x, self.d_data, self.d_invsig     # what the model kernels read
             nfold = self.ndata                 # leading entries of kd that form whole tiles
             fold_ok = self.usig and not os.environ.get('MC3B_NO_FOLD')
             if func.model_id == SINUSOID and self.dtype == _lib.F64 and x.size >= 8 \
@@ -188,7 +188,7 @@ class Population:
                 if x[-1] != x[0] and np.max(np.abs(x - ideal)) <= 8*np.finfo(float).eps*np.max(np.abs(x)):
                     self.chisq_model_id = SINUSOID_GRID
                     self.grid = True
-                elif fold_ok and not os.environ.get('MC3B_NO_SEG'):
+                elif not os.environ.get('MC3B_NO_SEG'):
                     # constant cadence with gaps: whole 128-point tiles first, the points
                     # that fill no tile last (include/mc3b200.h, tile_x)
                     self.seg = gridseg.tile_layout(x)
@@ -198,6 +198,8 @@ class Population:
                         with torch.cuda.device(self.dev):
                             perm = torch.from_numpy(self.seg['perm']).to(self.dev)
                             kx, kd = self.d_x[perm].contiguous(), self.d_data[perm].contiguous()
+                            if not self.usig:
+                                kw = self.d_invsig[perm].contiguous()
                             self.d_tile_x = torch.from_numpy(np.ascontiguousarray(x[self.seg['starts']])).to(self.dev)
                         nfold = 128*self.seg['starts'].size
             # with one uncertainty for all points the grid kernel works on point pairs
@@ -253,7 +255,7 @@ class Population:
                 self.k_x, self.k_d, self.k_w = (t.float().contiguous() for t in
                                                 (self.d_x, self.d_data, self.d_invsig))
             else:
-                self.k_x, self.k_d, self.k_w = kx, kd, self.d_invsig
+                self.k_x, self.k_d, self.k_w = kx, kd, kw
         elif self.shard == 'data':
             raise ValueError("shard='data' needs a built-in model")
         elif isinstance(func, TorchModel):

@@ -16,10 +16,13 @@ for lo, wd in ((20000, 3000), (50000, 10), (75000, 1), (99300, 300)):
 x, d = x[keep].copy(), d[keep].copy()
 x[x > 6.0] += 0.37*(w['x'][1] - w['x'][0])
 out = {'n': int(x.size)}
-for name, env in (('segmented', None), ('plain', 'MC3B_NO_SEG')):
+unc_pp = 0.5*np.random.RandomState(1).uniform(0.8, 1.25, x.size)
+for name, env, unc in (('segmented', None, np.full(x.size, 0.5)), ('segmented_per_point_sigma', None, unc_pp),
+                       ('plain', 'MC3B_NO_SEG', np.full(x.size, 0.5)), ('plain_per_point_sigma', 'MC3B_NO_SEG', unc_pp)):
+    os.environ.pop('MC3B_NO_SEG', None)
     if env:
         os.environ[env] = '1'
-    pop = Population(d, np.full(x.size, 0.5), mc3.models.sinusoid, w['params'], [x], {},
+    pop = Population(d, unc, mc3.models.sinusoid, w['params'], [x], {},
                      w['pstep'], w['pmin'], w['pmax'], w['prior'], w['priorlow'], w['priorup'],
                      nchains=4096, sampler='demc', fepsilon=0.01, thinning=1, nzchain=400, seed=3)
     pop.init_population('normal')

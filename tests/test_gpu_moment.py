@@ -267,3 +267,33 @@ def test_population_on_a_gapped_series(mc3, monkeypatch):
     assert np.array_equal(runs[0][0], runs[1][0])
     np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-10)
     assert np.array_equal(runs[0][2], runs[1][2])
+
+
+def test_population_on_a_gapped_series_with_per_point_uncertainties(mc3, monkeypatch):
+    """k_sinegrid<USIG=false> with tile origins: weights travel with the reordered points."""
+    from mc3_b200.engine import Population
+    x, rs = _gapped(40000, 9)
+    truth = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+    unc = rs.uniform(0.3, 0.8, x.size)
+    data = om.sinusoid(truth, x) + rs.normal(0, 1, x.size)*unc
+    kw = dict(pstep=np.array([1e-2, 1e-3, 1e-2, 1e-2, 1e-3]), pmin=np.array([0.0, 1.0, -np.pi, 0.0, -1.0]),
+              pmax=np.array([5.0, 5.0, np.pi, 10.0, 1.0]), nchains=256, sampler='demc', fepsilon=0.01,
+              nzchain=12, seed=5)
+    runs = []
+    for env in (None, 'MC3B_NO_SEG'):
+        if env:
+            monkeypatch.setenv(env, '1')
+        pop = Population(data, unc, mc3.models.sinusoid, truth*1.001, [x], {}, **kw)
+        assert (pop.seg is not None) == (env is None) and not pop.usig and pop.d_fold is None
+        P = truth*(1 + 0.01*np.random.RandomState(2).standard_normal((128, 5)))
+        P[::5, 1] = np.random.RandomState(3).uniform(3, 12, P[::5].shape[0])*(x[1] - x[0])
+        got = pop.chisq(torch.as_tensor(P, device=pop.dev)).cpu().numpy()
+        want = np.array([ok.chisq(om.sinusoid(p, x), data, unc) for p in P])
+        np.testing.assert_allclose(got, want, rtol=R64)
+        pop.init_population('normal')
+        pop.run(12)
+        torch.cuda.synchronize()
+        runs.append((pop.zchain.cpu().numpy(), pop.log_post.cpu().numpy(), pop.Z.cpu().numpy()))
+    assert np.array_equal(runs[0][0], runs[1][0])
+    np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-10)
+    assert np.array_equal(runs[0][2], runs[1][2])
