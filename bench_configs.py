@@ -330,13 +330,16 @@ def config5(args):
         if roof is None:
             P = pop.nextp[pop.chain0:pop.chain0 + pop.nlocal]
             moment = bool(getattr(pop, 'use_moment', False))
-            fuse = (pop.chain0, pop.gen, -1, False) if moment else None    # as the generation launches it
-            kms, _ = timed(torch, lambda: pop._data_chisq_local(P, fuse=fuse), reps=5, warm=1)
+            # as the generation launches it: fused with the Metropolis step (chains partitioned) or
+            # followed by the guarded finish (data sharded)
+            fuse = (pop.chain0, pop.gen, -1, False) if moment and pop.fused else None
+            kms, _ = timed(torch, lambda: pop._data_chisq_local(P, fuse, moment), reps=5, warm=1)
             peak = fp64_peak(torch, _lib)
             flops = float(w['flops_per_point'])*pop.nlocal*pop.ndata
             kname = 'k_model_chisq'
             if pop.grid:
-                kname = ('k_fold_consts + k_sinefold<MOM> + Metropolis epilogue' if moment else
+                kname = ('k_fold_consts + k_sinefold<MOM> + Metropolis epilogue' if moment and pop.fused else
+                         'k_fold_consts + k_sinefold<MOM> (guard in k_moment_finish, not timed)' if moment else
                          'k_fold_consts + k_sinefold' if getattr(pop, 'd_fold', None) is not None else
                          'k_sinegrid<USIG=%s>' % ('true' if pop.usig else 'false'))
             roof = {'bound': 'fp64', 'kernel': kname,

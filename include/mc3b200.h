@@ -111,8 +111,11 @@ int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp,
  *                the pair offsets, block and restart rotations) are then derived once per
  *                chain by a small kernel launched first, instead of by each of the nsplit
  *                CTAs of a chain group.  NULL: every CTA derives them (same bits).
- * moment         non-NULL (with uniform_sigma, fuse and work; fp64, MC3B_MODEL_SINUSOID_GRID):
- *                the sufficient-statistics form described at mc3b_moment_t below.
+ * moment         non-NULL (with uniform_sigma and work; fp64, MC3B_MODEL_SINUSOID_GRID):
+ *                the sufficient-statistics form described at mc3b_moment_t below.  Its rows
+ *                are UNGUARDED: either `fuse` is set (the Metropolis epilogue applies the
+ *                guard) or the rows go through mc3b_moment_finish, never through
+ *                mc3b_chisq_finish / mc3b_metropolis.
  * tile_x, dx, ntiles   (fp64, MC3B_MODEL_SINUSOID_GRID) PIECEWISE-uniform abscissa, e.g. a time series
  *                of constant cadence with gaps: the caller has reordered x and data so that
  *                (and invsig, when it is per point) so that
@@ -163,6 +166,18 @@ typedef struct mc3b_moment {
     double xlo, xhi;
     int32_t* guard_hits;
 } mc3b_moment_t;
+
+/* mc3b_chisq_finish for rows written by the moment form WITHOUT `fuse`: adds the
+ * nsplit rows of every chain in split order, applies the guard of mc3b_moment_t
+ * (re-evaluating the chains that fail it point by point from x, data, invsig[0],
+ * and counting them in *m->guard_hits), then adds the prior terms (prior may be NULL).
+ * params/ldp/x/data/invsig/n: as passed to mc3b_model_chisq_ex for the same launch. */
+int mc3b_moment_finish(const mc3b_moment_t* m, const double* partial,
+                       int64_t ldpartial, int nsplit, int64_t nchains,
+                       const double* params, int64_t ldp, int npars,
+                       const double* x, const double* data, const double* invsig,
+                       int64_t n, const double* prior, const double* priorlow,
+                       const double* priorup, double* chisq, void* stream);
 
 /* Chain-independent preparation for mc3b_moment_t over `ntiles` whole tiles of 128
  * points: x_i = x0 + i dx, or, with tile_x != NULL, tile_x[t] + j dx for point j of

@@ -81,6 +81,8 @@ _SIGS = {
                                     c_vp, c_vp, c_i64, c_vp, c_i64, c_int,
                                     ctypes.POINTER(ChisqOpts), c_vp]),
     'mc3b_fold_data': (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    'mc3b_moment_finish': (c_int, [ctypes.POINTER(MomentStruct), c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,
+                                   c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),

@@ -317,7 +317,7 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
                     A.xt = o.tile_x; A.dxg = o.dx; A.ntiles = o.ntiles;
                 }
                 if (usig && o.moment != nullptr) {
-                    MC3B_CHECK_ARG(A.f.on && o.work, "the moment form runs fused with the Metropolis step (fuse, work)");
+                    MC3B_CHECK_ARG(o.work, "the moment form needs the constants workspace (work)");
                     MC3B_CHECK_ARG(o.moment->folded && o.moment->tiles && o.moment->amp_max > 0.0 &&
                                    (((uintptr_t)o.moment->folded | (uintptr_t)o.moment->tiles) & 31) == 0,
                                    "bad moment data");
@@ -462,6 +462,22 @@ extern "C" int mc3b_model_chisq_ex(int model_id, int dtype, const double* params
 extern "C" int mc3b_fold_data(const double* data, int64_t n, double* out, void* stream) {
     MC3B_CHECK_ARG(data && out && n > 0, "bad fold arguments");
     return mc3b_launch_fold(data, n, out, (cudaStream_t)stream);
+}
+
+extern "C" int mc3b_moment_finish(const mc3b_moment_t* m, const double* partial, int64_t ldpartial, int nsplit,
+                                  int64_t nchains, const double* params, int64_t ldp, int npars, const double* x,
+                                  const double* data, const double* invsig, int64_t n, const double* prior,
+                                  const double* priorlow, const double* priorup, double* chisq, void* stream) {
+    MC3B_CHECK_ARG(m && partial && params && x && data && invsig && chisq, "null pointer");
+    MC3B_CHECK_ARG(nchains > 0 && nsplit > 0 && n > 0 && ldpartial >= nchains && ldp >= 5 && m->amp_max > 0.0,
+                   "bad moment_finish arguments");
+    MC3B_CHECK_ARG(prior == nullptr || (priorlow && priorup && npars > 0 && npars <= ldp), "bad prior arguments");
+    ChisqArgs<double> A = {};
+    A.params = params; A.ldp = ldp; A.nchains = nchains; A.x = x; A.d = data; A.w = invsig; A.n = n;
+    A.partial = const_cast<double*>(partial); A.ldpartial = ldpartial;
+    A.m.folded = m->folded; A.m.tiles = m->tiles; A.m.c0ref = m->c0ref; A.m.slref = m->slref;
+    A.m.d2tot = m->d2tot; A.m.amp_max = m->amp_max; A.m.xlo = m->xlo; A.m.xhi = m->xhi; A.m.guard_hits = m->guard_hits;
+    return mc3b_launch_moment_finish(A, nsplit, npars, prior, priorlow, priorup, chisq, (cudaStream_t)stream);
 }
 
 extern "C" int mc3b_moment_prepare(const double* data, int64_t ntiles, double x0, double dx, const double* tile_x,

@@ -179,5 +179,7 @@ using namespace mc3b_chisq;
 int mc3b_launch_sinegrid(const ChisqArgs<double>& a, bool usig, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_sinefold(const ChisqArgs<double>& a, double* work, unsigned groups, unsigned nsplit, cudaStream_t st);
 int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st);
+int mc3b_launch_moment_finish(const ChisqArgs<double>& a, int nsplit, int npars, const double* prior, const double* plo,
+                              const double* pup, double* chisq, cudaStream_t st);
 int mc3b_launch_moment_prepare(const double* d, int64_t ntiles, double x0, double dx, const double* tile_x,
                                double c0ref, double slref, double* folded, double* tiles, cudaStream_t st);

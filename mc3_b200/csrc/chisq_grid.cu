@@ -566,9 +566,40 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
     const double w0 = a.w[0];
     if (live) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = acc * (w0 * w0);
 #ifndef MC3B_NO_FUSE_CODE
-    if constexpr (MOM) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32, MomentFix{a});
-    else if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32);
+    if (a.f.on) {
+        if constexpr (MOM) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32, MomentFix{a});
+        else fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32);
+    }
 #endif
+}
+
+// mc3b_moment_finish: what the fused epilogue does for a launch WITHOUT the Metropolis step --
+// rows of k_sinefold<MOM> added in split order, the guard, the point-by-point
+// re-evaluation of the chains that fail it, then the prior terms (as k_chisq_finish).
+__global__ void __launch_bounds__(WARPS * 32) k_moment_finish(ChisqArgs<double> a, int nsplit, int npars,
+                                                              const double* __restrict__ prior,
+                                                              const double* __restrict__ plo,
+                                                              const double* __restrict__ pup, double* __restrict__ chisq) {
+    const int64_t c = (int64_t)blockIdx.x * (WARPS * 32) + threadIdx.x;
+    const bool mine = c < a.nchains;
+    double acc = 0.0;
+    if (mine)
+        for (int s = 0; s < nsplit; s++) acc += a.partial[(int64_t)s * a.ldpartial + c];
+    MomentFix{a}(mine, c, acc);
+    if (!mine) return;
+    if (prior != nullptr) {
+        double pr = 0.0;
+        for (int j = 0; j < npars; j++) {
+            const double lo = plo[j], up = pup[j];
+            if (lo > 0.0 && up > 0.0) {
+                const double off = a.params[c * a.ldp + j] - prior[j];
+                const double t = off / (off > 0.0 ? up : lo);
+                pr += t * t;
+            }
+        }
+        acc += pr;
+    }
+    chisq[c] = acc;
 }
 
 // out[16 b + 2 p] = -(d[16 b + 8 + p] + d[16 b + 7 - p])/2, out[16 b + 2 p + 1] = -(d[hi] - d[lo])/2
@@ -651,6 +682,14 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
         k_sinefold<true, false><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
     }
     MC3B_CHECK_LAUNCH("k_sinefold");
+    return MC3B_OK;
+}
+
+int mc3b_launch_moment_finish(const ChisqArgs<double>& a, int nsplit, int npars, const double* prior, const double* plo,
+                              const double* pup, double* chisq, cudaStream_t st) {
+    k_moment_finish<<<(unsigned)((a.nchains + WARPS * 32 - 1) / (WARPS * 32)), WARPS * 32, 0, st>>>(a, nsplit, npars, prior,
+                                                                                                  plo, pup, chisq);
+    MC3B_CHECK_LAUNCH("k_moment_finish");
     return MC3B_OK;
 }
 

@@ -220,7 +220,7 @@ class Population:
             # MC3B_NO_MOMENT=1 disables.
             self.moment = None
             self.use_moment = False
-            if self.d_fold is not None and self.shard == 'chains' and nfold >= 256 \
+            if self.d_fold is not None and nfold >= 256 \
                     and not os.environ.get('MC3B_NO_MOMENT') and not os.environ.get('MC3B_NO_FUSE'):
                 with torch.cuda.device(self.dev):
                     # least-squares line through the data and the sum of squares about it,
@@ -450,13 +450,32 @@ class Population:
         return torch.from_numpy(rows).to(self.dev)
 
     @on_device
-    def data_chisq(self, P, fuse=None):
+    def data_chisq(self, P, fuse=None, moment_ok=False):
         """(partial, ld, nsplit) holding the data chi-squared of rows of P.
         fuse = (c_off, gen, zrow0, advance): the model kernel also takes the
-        Metropolis step of chains c_off .. c_off + len(P) (built-in models)."""
+        Metropolis step of chains c_off .. c_off + len(P) (built-in models).
+        moment_ok: the caller sums the rows with _finish() (which applies the guard
+        of the sufficient-statistics form), not with mc3b_chisq_finish/mc3b_metropolis."""
         if self.shard == 'data':
             return self._data_chisq_sharded(P)
-        return self._data_chisq_local(P, fuse)
+        return self._data_chisq_local(P, fuse, moment_ok)
+
+    def _finish(self, part, ld, ns, nb, P, out, with_prior):
+        """out[c] = rows of `part` added in split order (+ prior terms): mc3b_chisq_finish, or
+        mc3b_moment_finish when the rows came from the unfused moment form."""
+        pr = (self.d_prior.data_ptr(), self.d_priorlow.data_ptr(),
+              self.d_priorup.data_ptr()) if (with_prior and self.has_prior) else (None, None, None)
+        if self._part_is_moment:
+            _lib.call('mc3b_moment_finish', ctypes.byref(self.moment), part.data_ptr(), ld, ns, nb,
+                      P.data_ptr(), _lib.ld(P), self.npars, self.k_x.data_ptr(), self.k_d.data_ptr(),
+                      self.k_w.data_ptr(), self.ndata, *pr, out.data_ptr(), _lib.stream_ptr())
+        elif with_prior:
+            _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, P.data_ptr(),
+                      _lib.ld(P), self.npars, *pr, out.data_ptr(), _lib.stream_ptr())
+        else:
+            _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, None, 0, 0,
+                      None, None, None, out.data_ptr(), _lib.stream_ptr())
+        self.launches += 1
 
     def _data_chisq_sharded(self, P):
         """Local-slice sums, then an all-gather of one fp64 per chain and device;
@@ -464,16 +483,16 @@ class Population:
         bits on every device)."""
         import torch.distributed as dist
         nb = P.shape[0]
-        part, ld, ns = self._data_chisq_local(P)
+        part, ld, ns = self._data_chisq_local(P, None, True)
         allsum = self._workspace(('allsum', nb), (self.world, nb))
-        _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, None, 0, 0,
-                  None, None, None, allsum[self.rank].data_ptr(), _lib.stream_ptr())
-        self.launches += 1
+        self._finish(part, ld, ns, nb, P, allsum[self.rank], False)
+        self._part_is_moment = False           # the gathered rows are plain sums
         dist.all_gather_into_tensor(allsum.view(-1), allsum[self.rank], group=self.group)
         return allsum, nb, self.world
 
-    def _data_chisq_local(self, P, fuse=None):
+    def _data_chisq_local(self, P, fuse=None, moment_ok=False):
         nb = P.shape[0]
+        self._part_is_moment = False
         st = _lib.stream_ptr()
         if self.wlike:
             out = self._workspace(('dwt', nb), (1, nb))
@@ -503,11 +522,13 @@ class Population:
                 o.ntiles = self.seg['starts'].size
             if self.d_fold is not None:
                 o.folded = self.d_fold.data_ptr()
-                if not os.environ.get('MC3B_NO_FOLD_CONSTS') or (fuse is not None and self.use_moment):
+                moment = self.use_moment and (fuse is not None or moment_ok)
+                if not os.environ.get('MC3B_NO_FOLD_CONSTS') or moment:
                     o.work = self._workspace(('foldk', nb), (_lib.FOLD_WORK, nb)).data_ptr()
                     self.launches += 1
-                if fuse is not None and self.use_moment:
+                if moment:
                     o.moment = ctypes.pointer(self.moment)
+                    self._part_is_moment = fuse is None
             if fuse is not None:
                 o.c_off, o.gen, o.zrow0, adv = fuse
                 o.advance = 1 if adv else 0
@@ -545,13 +566,9 @@ class Population:
         """chi-squared + prior terms of full parameter vectors P [nb, npars]."""
         P = P.contiguous()
         nb = P.shape[0]
-        part, ld, ns = self.data_chisq(P)
+        part, ld, ns = self.data_chisq(P, moment_ok=True)
         out = torch.empty(nb, dtype=torch.float64, device=self.dev)
-        pr = (self.d_prior.data_ptr(), self.d_priorlow.data_ptr(),
-              self.d_priorup.data_ptr()) if self.has_prior else (None, None, None)
-        _lib.call('mc3b_chisq_finish', part.data_ptr(), ld, ns, nb, P.data_ptr(),
-                  _lib.ld(P), self.npars, *pr, out.data_ptr(), _lib.stream_ptr())
-        self.launches += 1
+        self._finish(part, ld, ns, nb, P, out, True)
         return out
 
     # ------------------------------------------------------------------

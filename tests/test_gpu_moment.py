@@ -297,3 +297,24 @@ def test_population_on_a_gapped_series_with_per_point_uncertainties(mc3, monkeyp
     assert np.array_equal(runs[0][0], runs[1][0])
     np.testing.assert_allclose(runs[0][1], runs[1][1], rtol=1e-10)
     assert np.array_equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.parametrize('snr', [2.0, 3000.0])
+def test_unfused_moment_form_with_guarded_finish(mc3, snr):
+    """Population.chisq() (initial population, statistics, data shard): k_sinefold<MOM> without
+    the Metropolis epilogue, rows summed by mc3b_moment_finish -- which must re-evaluate what
+    the expansion cannot deliver (high S/N) and leave the rest alone (low S/N)."""
+    pop, x, data, sigma = _population(mc3, 30000 + 41, snr, 5.0, nchains=256)
+    assert pop.use_moment
+    rs = np.random.RandomState(4)
+    truth = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+    P = truth*(1 + 0.01/snr*rs.standard_normal((300, 5)))
+    P[:20] = truth*(1 + 0.3*rs.standard_normal((20, 5)))          # far from the mode as well
+    P[:, 1] = np.clip(P[:, 1], 1.2, 4.5)
+    h0 = int(pop.guard_hits.item())
+    got = pop.chisq(torch.as_tensor(P, device=pop.dev)).cpu().numpy()
+    want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+    want += ((P[:, 1] - 2.5)/np.where(P[:, 1] > 2.5, 0.2, 0.1))**2
+    np.testing.assert_allclose(got, want, rtol=R64)
+    hits = int(pop.guard_hits.item()) - h0
+    assert hits == 0 if snr < 10 else hits >= 250
