@@ -139,7 +139,7 @@ typedef struct mc3b_chisq_opts {
     double dx;
     int64_t ntiles;
 } mc3b_chisq_opts_t;
-#define MC3B_FOLD_WORK 25
+#define MC3B_FOLD_WORK 27
 
 /* Sufficient-statistics form of the uniform-grid sinusoid + line chi-squared (one
  * uncertainty for all points).  With the data centred on a reference line,
@@ -158,6 +158,9 @@ typedef struct mc3b_chisq_opts {
  *   c0ref, slref   the reference line (any; a least-squares line through the data keeps amp small)
  *   d2tot   sum of d'^2 over the n points     amp_max  e.g. 4000 (error < 1.2e-11)
  *   xlo, xhi  smallest and largest abscissa (they bound |L'|)
+ *   layout  of `folded`: 0 = pairs interleaved as in mc3b_fold_data (Pe, Po by FMAs),
+ *           1 = the four B fragments of mma.m8n8k4 per tile (Pe, Po as FP64 tensor-core
+ *           products: fewer operand reads, instructions and shared-memory loads)
  *   guard_hits  device int32 counter or NULL */
 typedef struct mc3b_moment {
     const double* folded;
@@ -165,6 +168,7 @@ typedef struct mc3b_moment {
     double c0ref, slref, d2tot, amp_max;
     double xlo, xhi;
     int32_t* guard_hits;
+    int32_t layout;     /* as given to mc3b_moment_prepare */
 } mc3b_moment_t;
 
 /* mc3b_chisq_finish for rows written by the moment form WITHOUT `fuse`: adds the
@@ -182,12 +186,13 @@ int mc3b_moment_finish(const mc3b_moment_t* m, const double* partial,
 /* Chain-independent preparation for mc3b_moment_t over `ntiles` whole tiles of 128
  * points: x_i = x0 + i dx, or, with tile_x != NULL, tile_x[t] + j dx for point j of
  * tile t (piecewise-uniform abscissa, see mc3b_chisq_opts_t).  Per 16-point
- * block, pair p joins points 7-p and 8+p: folded[16 b + 2 p] = -(d'_hi + d'_lo),
- * folded[16 b + 2 p + 1] = -(d'_hi - d'_lo); per 128-point tile t,
+ * block, pair p joins points 7-p and 8+p: layout 0: folded[16 b + 2 p] = -(d'_hi + d'_lo),
+ * folded[16 b + 2 p + 1] = -(d'_hi - d'_lo); layout 1: within the tile, entry
+ * 64 eo + 32 (p / 4) + 4 b + p % 4 (eo = 0 for the sums, 1 for the differences); per tile t,
  * tiles[4 t ..] = {-2 sum e, -2 (16 sum_b (b - 3.5) sum_p e + sum (p + 1/2) o), sum e^2 + o^2, 0}
  * with e, o the half sum and half difference of a pair. */
 int mc3b_moment_prepare(const double* data, int64_t ntiles, double x0, double dx,
-                        const double* tile_x, double c0ref, double slref,
+                        const double* tile_x, double c0ref, double slref, int layout,
                         double* folded, double* tiles, void* stream);
 
 /* Chain-independent preparation for `folded` above: per block of 16 points, pair

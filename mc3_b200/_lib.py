@@ -46,7 +46,7 @@ class MomentStruct(ctypes.Structure):
     """mc3b_moment_t."""
     _fields_ = [('folded', c_vp), ('tiles', c_vp), ('c0ref', c_dbl), ('slref', c_dbl),
                 ('d2tot', c_dbl), ('amp_max', c_dbl), ('xlo', c_dbl), ('xhi', c_dbl),
-                ('guard_hits', c_vp)]
+                ('guard_hits', c_vp), ('layout', c_i32)]
 
 
 class ChisqOpts(ctypes.Structure):
@@ -58,7 +58,7 @@ class ChisqOpts(ctypes.Structure):
                 ('ntiles', c_i64)]
 
 
-FOLD_WORK = 25                    # MC3B_FOLD_WORK
+FOLD_WORK = 27                    # MC3B_FOLD_WORK
 
 
 class DrawsStruct(ctypes.Structure):
@@ -83,7 +83,7 @@ _SIGS = {
     'mc3b_fold_data': (c_int, [c_vp, c_i64, c_vp, c_vp]),
     'mc3b_moment_finish': (c_int, [ctypes.POINTER(MomentStruct), c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,
                                    c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    'mc3b_moment_prepare': (c_int, [c_vp, c_i64, c_dbl, c_dbl, c_vp, c_dbl, c_dbl, c_int, c_vp, c_vp, c_vp]),
     'mc3b_model_eval': (c_int, [c_int, c_vp, c_i64, c_i64, c_int, c_vp, c_i64,
                                 c_vp, c_vp]),
     'mc3b_chisq_finish': (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_i64, c_int,

@@ -324,7 +324,8 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
                     A.m.folded = o.moment->folded; A.m.tiles = o.moment->tiles;
                     A.m.c0ref = o.moment->c0ref; A.m.slref = o.moment->slref; A.m.d2tot = o.moment->d2tot;
                     A.m.amp_max = o.moment->amp_max; A.m.guard_hits = o.moment->guard_hits;
-                    A.m.xlo = o.moment->xlo; A.m.xhi = o.moment->xhi;
+                    A.m.xlo = o.moment->xlo; A.m.xhi = o.moment->xhi; A.m.layout = o.moment->layout;
+                    MC3B_CHECK_ARG(A.m.layout == 0 || A.m.layout == 1, "bad moment layout %d", A.m.layout);
                     return mc3b_launch_sinefold(A, (double*)o.work, (unsigned)groups, (unsigned)nsplit, st);
                 }
                 if (usig && A.fold != nullptr && ((uintptr_t)A.fold & 15) == 0)
@@ -481,10 +482,11 @@ extern "C" int mc3b_moment_finish(const mc3b_moment_t* m, const double* partial,
 }
 
 extern "C" int mc3b_moment_prepare(const double* data, int64_t ntiles, double x0, double dx, const double* tile_x,
-                                   double c0ref, double slref, double* folded, double* tiles, void* stream) {
+                                   double c0ref, double slref, int layout, double* folded, double* tiles, void* stream) {
     MC3B_CHECK_ARG(data && folded && tiles && ntiles >= 0, "bad moment_prepare arguments");
+    MC3B_CHECK_ARG(layout == 0 || layout == 1, "bad moment layout %d", layout);
     MC3B_CHECK_ARG((((uintptr_t)tiles) & 31) == 0, "tiles must be 32-byte aligned");
-    return mc3b_launch_moment_prepare(data, ntiles, x0, dx, tile_x, c0ref, slref, folded, tiles, (cudaStream_t)stream);
+    return mc3b_launch_moment_prepare(data, ntiles, x0, dx, tile_x, c0ref, slref, folded, tiles, layout, (cudaStream_t)stream);
 }
 
 extern "C" int mc3b_model_chisq(int model_id, int dtype, const double* params, int64_t ldp, int64_t nchains,

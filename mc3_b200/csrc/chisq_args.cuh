@@ -52,6 +52,7 @@ struct MomentArgs {
     double c0ref, slref, d2tot, amp_max;
     double xlo, xhi;                // range of the abscissa (bound of the line term of the guard)
     int32_t* guard_hits;
+    int layout;                     // of `folded`: 0 pairs interleaved (k_sinefold<MOM>), 1 mma fragments (k_sinemma)
 };
 
 template <typename T> struct ChisqArgs {
@@ -182,4 +183,4 @@ int mc3b_launch_fold(const double* d, int64_t n, double* out, cudaStream_t st);
 int mc3b_launch_moment_finish(const ChisqArgs<double>& a, int nsplit, int npars, const double* prior, const double* plo,
                               const double* pup, double* chisq, cudaStream_t st);
 int mc3b_launch_moment_prepare(const double* d, int64_t ntiles, double x0, double dx, const double* tile_x,
-                               double c0ref, double slref, double* folded, double* tiles, cudaStream_t st);
+                               double c0ref, double slref, double* folded, double* tiles, int layout, cudaStream_t st);

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_GRID_MINB) k_sinegrid(ChisqAr
 // then start with one round of coalesced loads.  Same formulas, same bits.
 namespace fold {
 constexpr int BLK = 16, NP = BLK / 2;
-constexpr int NCONST = 2 * NP + 9;      // k, cp[NP], sp[NP], c16, s16, cdT, sdT, Kcc, Kc2, Kss, Ksd2
+constexpr int NCONST = 2 * NP + 11;     // k, cp[NP], sp[NP], c16, s16, cdT, sdT, Kcc, Kc2, Kss, Ksd2, c128, s128
 static_assert(NCONST == MC3B_FOLD_WORK, "include/mc3b200.h: MC3B_FOLD_WORK");
 struct Consts { double k, cp[NP], sp[NP], c16, s16, cdT, sdT; };
 __device__ __forceinline__ void derive(double period, double dx, Consts& K) {
@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(128) k_fold_consts(const double* __restrict__ 
     o[(3 + 2 * NP) * ld] = K.cdT; o[(4 + 2 * NP) * ld] = K.sdT;
     o[(5 + 2 * NP) * ld] = kcc; o[(6 + 2 * NP) * ld] = 2.0 * kc;
     o[(7 + 2 * NP) * ld] = kss; o[(8 + 2 * NP) * ld] = 2.0 * ksd;
+    double s128, c128;                                      // one tile on (k_sinemma)
+    fast_sincos_core((double)grid::TILE * (K.k * dx), s128, c128);
+    o[(9 + 2 * NP) * ld] = c128; o[(10 + 2 * NP) * ld] = s128;
 }
 
 // ---- MOM: the same sum from sufficient statistics -------------------------------------
@@ -573,6 +576,207 @@ __global__ void __launch_bounds__(WARPS * 32, MC3B_FOLD_MINB) k_sinefold(ChisqAr
 #endif
 }
 
+// ---- k_sinemma: the moment form with Pe, Po as FP64 tensor-core products ----------------
+// Pe[chain, block] = sum_p cos(dl_p h_chain) e[p, block] is an [8 chains x 8 pairs] x [8 pairs x
+// 8 blocks] product per 128-point tile: two mma.m8n8k4 (k = pairs 0-3, 4-7), two more for
+// Po.  DMMA runs on the FP64 FMA units at the same flop rate (profiles/r2_fp64_probe.md), but
+// an m8n8k4 reads four operand registers for 256 FMAs where 128 DFMAs read 384, needs 4
+// instructions instead of 128, and its B fragments are four conflict-free LDS.64 per lane
+// and tile instead of 64 LDS.128 -- the DFMA form is bound by exactly those (operand reads,
+// issue slots, shared-memory latency), not by the pipe.
+// Mapping: a warp owns 8 chains (lane l: chain l >> 2) and, per tile, lane l ends up with Pe, Po
+// of blocks 2 (l & 3) and 2 (l & 3) + 1 of its chain: the per-block work (rotation of (Sc, Cc),
+// block line, the four FMAs that fold Pe, Po into the sum) is spread over the chain's four
+// lanes, and each lane keeps ONE chain's constants.  The CTA covers its 128 chains in four
+// passes of 32 over the split's tiles (the TMA ring just keeps turning: the tile sequence
+// repeats), so the launch shape, the partial rows and the Metropolis epilogue are those of
+// k_sinefold.
+#ifndef MC3B_MMA_MINB
+#define MC3B_MMA_MINB 4
+#endif
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(WARPS * 32, MC3B_MMA_MINB) k_sinemma(ChisqArgs<double> a) {
+    using namespace grid;
+    using fold::BLK; using fold::NP;
+    static_assert(WARPS == 4 && TILE == 128 && NP == 8, "four warps x 8 chains x 4 passes = 128 chains; one n8 tile");
+    // One iteration = up to NT4 consecutive tiles (one TMA stage): the per-iteration work
+    // (barrier waits, addresses, anchors) is paid once per 4 x 128 points x 8 chains per warp.
+    constexpr int NT4 = 4;
+    static_assert(NT4 == RESTART, "an iteration is one restart interval of the anchors");
+    asm volatile("griddepcontrol.launch_dependents;");
+    __shared__ __align__(128) double sf[NSTAGE][NT4 * TILE];
+    __shared__ __align__(32) double sm[NSTAGE][NT4 * 4];
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q4 = lane & 3;
+    const bool seg = a.xt != nullptr;
+    const int64_t nfull = seg ? a.ntiles : a.n / TILE;
+    int64_t tb, te;
+    if (a.nsched > 0) { tb = a.tstart[blockIdx.y]; te = a.tstart[blockIdx.y + 1]; }
+    else { tb = (a.n / TILE) * blockIdx.y / gridDim.y; te = (a.n / TILE) * (blockIdx.y + 1) / gridDim.y; }
+    if (tb > nfull) tb = nfull;
+    if (te > nfull) te = nfull;
+    const int64_t nt = te - tb;
+    const int64_t npi = (nt + NT4 - 1) / NT4, nit = 4 * npi;      // iterations per pass; four passes over the same tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int64_t it, int s) {
+        const int64_t t = tb + (it % npi) * NT4;
+        const int64_t cnt = te - t < NT4 ? te - t : NT4;
+        mbar_expect_tx(&full[s], (uint32_t)(cnt * (TILE + 4) * sizeof(double)));
+        bulk_g2s(sf[s], a.m.folded + t * TILE, (uint32_t)(cnt * TILE * sizeof(double)), &full[s]);
+        bulk_g2s(sm[s], a.m.tiles + t * 4, (uint32_t)(cnt * 4 * sizeof(double)), &full[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < NSTAGE && s < nit; s++) issue(s, s);
+
+    const double x0 = a.x[0];
+    const double dx = seg ? a.dxg : (a.x[a.n - 1] - x0) / (double)(a.n - 1);
+    const double w0 = a.w[0];
+    if (a.consts_wait) asm volatile("griddepcontrol.wait;" ::: "memory");       // k_fold_consts has completed
+
+    int64_t it = 0;
+    for (int pass = 0; pass < 4; pass++) {
+        int64_t c = (int64_t)blockIdx.x * (WARPS * 32) + pass * 32 + warp * 8 + g;
+        const bool live = c < a.nchains;
+        if (!live) c = a.nchains - 1;
+        const double* p = a.params + c * a.ldp;
+        const double amp = p[0], ph = p[2], c0 = p[3], sl = p[4];
+        const double c0r = c0 - a.m.c0ref, slr = sl - a.m.slref;
+        const double* kc = a.consts + c;
+        const double k = kc[0];
+        const double cpa0 = kc[(1 + q4) * a.ldc], cpa1 = kc[(5 + q4) * a.ldc];                 // A fragments
+        const double spa0 = kc[(1 + NP + q4) * a.ldc], spa1 = kc[(5 + NP + q4) * a.ldc];
+        const double c16 = kc[(1 + 2 * NP) * a.ldc], s16 = kc[(2 + 2 * NP) * a.ldc];
+        const double cdT = kc[(3 + 2 * NP) * a.ldc], sdT = kc[(4 + 2 * NP) * a.ldc];
+        const double Kcc = kc[(5 + 2 * NP) * a.ldc], Kc2 = kc[(6 + 2 * NP) * a.ldc];
+        const double Kss = kc[(7 + 2 * NP) * a.ldc];
+        const double c128 = kc[(9 + 2 * NP) * a.ldc], s128 = kc[(10 + 2 * NP) * a.ldc];
+        const double dth = k * dx;
+        const double gs = slr * dx, dL16 = (double)BLK * gs, dL128 = (double)TILE * gs;
+        const double gK = kc[(8 + 2 * NP) * a.ldc] * gs;                                        // 2 g Ksd
+        const int keybase = sin_arg_key((double)(NT4 * TILE) * dth) >= MC3B_SIN_KEY_LIMIT ? MC3B_SIN_KEY_LIMIT : 0;
+        auto direct = [&](double x) { return fma(amp, sin(fma(x, k, ph)), fma(sl, x, c0)); };
+        const double boff = (double)(2 * q4 * BLK) + 7.5;       // centre of this lane's first block of a tile, in points
+
+        double acc = 0.0, S0 = 0.0, C0 = 0.0;
+        int rcount = 0;
+        for (int64_t ji = 0; ji < npi; ji++, it++) {
+            const int st = (int)(it % NSTAGE);
+            const uint32_t par = (uint32_t)((it / NSTAGE) & 1);
+            const int64_t t0 = tb + ji * NT4;
+            const int cnt = (int)(te - t0 < NT4 ? te - t0 : NT4);
+            // anchor of the iteration: this lane's first block of its first tile
+            const double xo = seg ? a.xt[t0] : fma((double)(t0 * TILE), dx, x0);
+            const double xc = fma(boff, dx, xo);
+            const double th = fma(xc, k, ph);
+            int key = max(keybase, max(sin_arg_key(th), sin_arg_key(fma((double)(NT4 * TILE), dth, th))));
+            if (rcount == 0 || seg) {
+                fast_sincos_core(th, S0, C0);
+                S0 *= amp; C0 *= amp;
+            } else {
+                const double sn = fma(C0, sdT, S0 * cdT);
+                C0 = fma(-S0, sdT, C0 * cdT);
+                S0 = sn;
+            }
+            rcount = (rcount + 1 == REANCHOR) ? 0 : rcount + 1;
+            double Sc = S0, Cc = C0;
+            const double L00 = fma(slr, xc, c0r);       // line at the centre of that block
+            double q = 0.0;
+            mbar_wait(&full[st], par);
+#pragma unroll
+            for (int u = 0; u < NT4; u++) {
+                if (u < cnt) {                          // (uniform over the CTA: the MMAs stay warp-wide)
+                    double L0 = u == 0 ? L00 : fma(dL128, (double)u, L00);
+                    if (u > 0) {
+                        if (seg) {                      // tiles of a piecewise-uniform abscissa have their own origins
+                            const double xcu = fma(boff, dx, a.xt[t0 + u]);
+                            const double thu = fma(xcu, k, ph);
+                            key = max(key, sin_arg_key(thu));
+                            fast_sincos_core(thu, Sc, Cc);
+                            Sc *= amp; Cc *= amp;
+                            L0 = fma(slr, xcu, c0r);
+                        } else {                        // one tile on
+                            const double sn = fma(Cc, s128, Sc * c128);
+                            Cc = fma(-Sc, s128, Cc * c128);
+                            Sc = sn;
+                        }
+                    }
+                    const double L1 = L0 + dL16;
+                    const double* ft = sf[st] + u * TILE;
+                    double pe0 = L0 * Kc2, pe1 = L1 * Kc2, po0 = gK, po1 = gK;     // 2 Lc Kc - 2 Pe ; 2 g Ksd - 2 Po
+                    dmma884(pe0, pe1, cpa0, ft[lane]);
+                    dmma884(po0, po1, spa0, ft[64 + lane]);
+                    dmma884(pe0, pe1, cpa1, ft[32 + lane]);
+                    dmma884(po0, po1, spa1, ft[96 + lane]);
+                    const double S1 = fma(Cc, s16, Sc * c16), C1 = fma(-Sc, s16, Cc * c16);   // the second block
+                    q = fma(Sc, fma(Sc, Kcc, pe0), q);
+                    q = fma(Cc, fma(Cc, Kss, po0), q);
+                    q = fma(S1, fma(S1, Kcc, pe1), q);
+                    q = fma(C1, fma(C1, Kss, po1), q);
+                    if (u == q4) {
+                        // line and data terms of tile u from its three moments (one of the chain's lanes each):
+                        //   64 Lm^2 + 87376 g^2 - 2 Lm M0 - 2 g M1 + M2,  Lm = line at the tile centre
+                        const double4 mo = *reinterpret_cast<const double4*>(sm[st] + 4 * u);
+                        const double Lm = fma(gs, 63.5 - boff, L0);
+                        q += fma(Lm, fma(Lm, 64.0, mo.x), mo.z) + gs * fma(gs, 87376.0, mo.y);
+                    }
+                }
+            }
+            if (key >= MC3B_SIN_KEY_LIMIT) {            // guarded chains: library sine per point, raw data
+                double qd = 0.0;
+                for (int u = 0; u < cnt; u++) {
+                    const double xou = seg ? a.xt[t0 + u] : fma((double)((t0 + u) * TILE), dx, x0);
+                    const double* dt = a.d + (t0 + u) * TILE;
+                    for (int i = q4; i < TILE; i += 4) {
+                        const double r = direct(fma((double)i, dx, xou)) - dt[i];
+                        qd = fma(r, r, qd);
+                    }
+                }
+                q = 0.5 * qd;
+            }
+            acc += q;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+            if (threadIdx.x == 0 && it >= 1 && it - 1 + NSTAGE < nit) {
+                const int sq = (int)((it - 1) % NSTAGE);
+                mbar_wait(&empty[sq], (uint32_t)(((it - 1) / NSTAGE) & 1));
+                issue(it - 1 + NSTAGE, sq);
+            }
+        }
+        acc *= 2.0;
+        // points outside the tiles (ragged tail: last split; piecewise-uniform: shared out over the
+        // splits), every fourth point to each of the chain's lanes
+        {
+            int64_t lb = nfull * TILE, le = a.n;
+            if (seg) {
+                const int64_t nl = a.n - nfull * TILE;
+                lb = nfull * TILE + nl * blockIdx.y / gridDim.y; le = nfull * TILE + nl * (blockIdx.y + 1) / gridDim.y;
+            } else if (blockIdx.y != gridDim.y - 1) le = lb;
+            double t = 0.0;
+            for (int64_t i = lb + q4; i < le; i += 4) {
+                const double r = direct(a.x[i]) - a.d[i];
+                t = fma(r, r, t);
+            }
+            acc += t;
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (live && q4 == 0) a.partial[(int64_t)blockIdx.y * a.ldpartial + c] = acc * (w0 * w0);
+    }
+#ifndef MC3B_NO_FUSE_CODE
+    if (a.f.on) fused_metropolis(a.f, a.partial, a.ldpartial, a.nchains, WARPS * 32, MomentFix{a});
+#endif
+}
+
 // mc3b_moment_finish: what the fused epilogue does for a launch WITHOUT the Metropolis step --
 // rows of k_sinefold<MOM> added in split order, the guard, the point-by-point
 // re-evaluation of the chains that fail it, then the prior terms (as k_chisq_finish).
@@ -616,9 +820,12 @@ __global__ void k_fold(const double* __restrict__ d, int64_t nblk16, double* __r
 // block l >> 2.  d' = d - (c0ref + slref x_i); folded[.] = -2 e, -2 o (e, o = half sum and
 // half difference of a pair); tiles[t] = {-2 sum e, -2 (16 sum_b (b - 3.5) E1_b + sum dl o),
 // sum e^2 + o^2, 0}.  Fixed-order shuffles: same bits on every run.
+// layout 1 (k_sinemma): the tile as the four B fragments of mma.m8n8k4 -- entry
+// eo*64 + ks*32 + 4 b + q holds pair p = 4 ks + q of block b (eo = 0: -2 e, 1: -2 o), so
+// that lane l = 4 b + q of a warp reads its element of fragment (eo, ks) at offset l.
 __global__ void __launch_bounds__(128) k_moment_prepare(const double* __restrict__ d, int64_t ntiles, double x0, double dx,
                                                         const double* __restrict__ tile_x, double c0ref, double slref,
-                                                        double* __restrict__ folded, double* __restrict__ tiles) {
+                                                        double* __restrict__ folded, double* __restrict__ tiles, int layout) {
     const int64_t t = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (t >= ntiles) return;
     const int lane = threadIdx.x & 31, b = lane >> 2;
@@ -631,8 +838,13 @@ __global__ void __launch_bounds__(128) k_moment_prepare(const double* __restrict
         const double lo = d[ilo] - fma(slref, fma((double)(b * 16 + 7 - pp), dx, xo), c0ref);
         const double hi = d[ihi] - fma(slref, fma((double)(b * 16 + 8 + pp), dx, xo), c0ref);
         const double e = 0.5 * (hi + lo), o = 0.5 * (hi - lo);
-        folded[t * 128 + b * 16 + 2 * pp] = -2.0 * e;
-        folded[t * 128 + b * 16 + 2 * pp + 1] = -2.0 * o;
+        if (layout == 0) {
+            folded[t * 128 + b * 16 + 2 * pp] = -2.0 * e;
+            folded[t * 128 + b * 16 + 2 * pp + 1] = -2.0 * o;
+        } else {
+            folded[t * 128 + (pp >> 2) * 32 + b * 4 + (pp & 3)] = -2.0 * e;
+            folded[t * 128 + 64 + (pp >> 2) * 32 + b * 4 + (pp & 3)] = -2.0 * o;
+        }
         m0 += e;
         m1 += fma(16.0 * ((double)b - 3.5), e, ((double)pp + 0.5) * o);
         m2 += fma(e, e, o * o);
@@ -674,8 +886,11 @@ int mc3b_launch_sinefold(const ChisqArgs<double>& a0, double* work, unsigned gro
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        if (mom) MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true, true>, a));
+        if (mom && a.m.layout == 1) MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinemma, a));
+        else if (mom) MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true, true>, a));
         else MC3B_CUDA(cudaLaunchKernelEx(&cfg, k_sinefold<true, false>, a));
+    } else if (mom && a.m.layout == 1) {
+        k_sinemma<<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
     } else if (mom) {
         k_sinefold<true, true><<<dim3(groups, nsplit), WARPS * 32, 0, st>>>(a);
     } else {
@@ -694,9 +909,9 @@ int mc3b_launch_moment_finish(const ChisqArgs<double>& a, int nsplit, int npars,
 }
 
 int mc3b_launch_moment_prepare(const double* d, int64_t nt, double x0, double dx, const double* tile_x, double c0ref,
-                               double slref, double* folded, double* tiles, cudaStream_t st) {
+                               double slref, double* folded, double* tiles, int layout, cudaStream_t st) {
     if (nt == 0) return MC3B_OK;
-    k_moment_prepare<<<(unsigned)((nt + 3) / 4), 128, 0, st>>>(d, nt, x0, dx, tile_x, c0ref, slref, folded, tiles);
+    k_moment_prepare<<<(unsigned)((nt + 3) / 4), 128, 0, st>>>(d, nt, x0, dx, tile_x, c0ref, slref, folded, tiles, layout);
     MC3B_CHECK_LAUNCH("k_moment_prepare");
     return MC3B_OK;
 }

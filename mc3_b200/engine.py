@@ -235,8 +235,11 @@ class Population:
                     self.d_mtiles = torch.zeros((max(nfold//128, 1), 4), **f64)
                     self.guard_hits = torch.zeros(1, dtype=torch.int32, device=self.dev)
                     dxg = self.seg['dx'] if self.seg else float((x[-1] - x[0])/(x.size - 1))
+                    # MC3B_MOM_LAYOUT=1: Pe, Po as FP64 tensor-core products (k_sinemma) instead of
+                    # FMAs (k_sinefold<MOM>): correct, measured slower (0.127 against 0.099 ms at config 2)
+                    layout = int(os.environ.get('MC3B_MOM_LAYOUT', 0))
                     _lib.call('mc3b_moment_prepare', kd.data_ptr(), nfold//128, float(x[0]), dxg,
-                              self.d_tile_x.data_ptr() if self.seg else None, c0r, slr,
+                              self.d_tile_x.data_ptr() if self.seg else None, c0r, slr, layout,
                               self.d_mfold.data_ptr(), self.d_mtiles.data_ptr(), _lib.stream_ptr())
                 M = _lib.MomentStruct()
                 M.folded, M.tiles = self.d_mfold.data_ptr(), self.d_mtiles.data_ptr()
@@ -244,6 +247,7 @@ class Population:
                 M.amp_max = float(os.environ.get('MC3B_MOMENT_AMP', 4000.0))
                 M.xlo, M.xhi = float(x.min()), float(x.max())
                 M.guard_hits = self.guard_hits.data_ptr()
+                M.layout = layout
                 self.moment = M
                 self.use_moment = True
                 self._guard_log = []          # (generation, ring slot) per run() call, oldest first

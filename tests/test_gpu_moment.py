@@ -39,15 +39,23 @@ def test_moment_prepare_matches_numpy(mc3):
         dd = torch.from_numpy(d).to(dev)
         df = torch.full((n,), 7.0, dtype=torch.float64, device=dev)
         dt = torch.zeros((n//128, 4), dtype=torch.float64, device=dev)
-        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, x0, dx, None, c0r, slr, df.data_ptr(),
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, x0, dx, None, c0r, slr, 0, df.data_ptr(),
                   dt.data_ptr(), _lib.stream_ptr())
         # the same tiles addressed through their origins (piecewise-uniform layout)
         tx = torch.from_numpy(x0 + 128*dx*np.arange(n//128)).to(dev)
         df2, dt2 = torch.full_like(df, 7.0), torch.zeros_like(dt)
-        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, 0.0, dx, tx.data_ptr(), c0r, slr,
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, 0.0, dx, tx.data_ptr(), c0r, slr, 0,
                   df2.data_ptr(), dt2.data_ptr(), _lib.stream_ptr())
         np.testing.assert_allclose(df2.cpu().numpy(), df.cpu().numpy(), rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(dt2.cpu().numpy(), dt.cpu().numpy(), rtol=1e-10, atol=1e-10)
+        # layout 1 (mma fragments): the same numbers, entry 64 eo + 32 (p / 4) + 4 b + p % 4 of each tile
+        df3, dt3 = torch.full_like(df, 7.0), torch.zeros_like(dt)
+        _lib.call('mc3b_moment_prepare', dd.data_ptr(), n//128, x0, dx, None, c0r, slr, 1,
+                  df3.data_ptr(), dt3.data_ptr(), _lib.stream_ptr())
+        l0 = df.cpu().numpy()[:n//128*128].reshape(-1, 8, 8, 2)            # tile, block, pair, (e, o)
+        l1 = df3.cpu().numpy()[:n//128*128].reshape(-1, 2, 2, 8, 4)        # tile, eo, ks, block, q
+        assert np.array_equal(l1, l0.reshape(-1, 8, 2, 4, 2).transpose(0, 4, 2, 1, 3))
+        assert np.array_equal(dt3.cpu().numpy(), dt.cpu().numpy())
         nt = n//128*128
         np.testing.assert_allclose(df.cpu().numpy()[:nt], f, rtol=1e-13, atol=1e-14)
         assert np.all(df.cpu().numpy()[nt:] == 7.0)
@@ -318,3 +326,31 @@ def test_unfused_moment_form_with_guarded_finish(mc3, snr):
     np.testing.assert_allclose(got, want, rtol=R64)
     hits = int(pop.guard_hits.item()) - h0
     assert hits == 0 if snr < 10 else hits >= 250
+
+
+def test_tensor_core_form_of_the_moment_kernel(mc3, monkeypatch):
+    """MC3B_MOM_LAYOUT=1: k_sinemma (Pe, Po by mma.m8n8k4 on the B-fragment layout of the
+    folded data) against the oracle, fused and unfused, low S/N and through the guard."""
+    monkeypatch.setenv('MC3B_MOM_LAYOUT', '1')
+    for n, snr in ((100000, 2.0), (20000 + 77, 3000.0), (1000, 1.0)):
+        pop, x, data, sigma = _population(mc3, n, snr, 5.0)
+        assert pop.use_moment and pop.moment.layout == 1
+        pop.init_population('normal')                    # unfused launches + mc3b_moment_finish
+        pop.use_moment = True
+        pop.gen_dev.fill_(0)
+        for gen in range(2):
+            P, got, inb, before, after = _one_generation(pop, gen)
+            want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in P])
+            prior = ((P[:, 1] - 2.5)/np.where(P[:, 1] > 2.5, 0.2, 0.1))**2
+            if snr < 10:
+                np.testing.assert_allclose(got[inb], want[inb], rtol=R64)
+            moved = after != before
+            assert moved.any()
+            np.testing.assert_allclose(after[moved], (want + prior)[moved], rtol=R64)
+        assert (int(pop.guard_hits.item()) == 0) == (snr < 10)
+        rs = np.random.RandomState(0)
+        Pq = P[rs.choice(P.shape[0], 64, replace=False)]
+        got = pop.chisq(torch.as_tensor(Pq, device=pop.dev)).cpu().numpy()
+        want = np.array([np.sum(((om.sinusoid(p, x) - data)/sigma)**2) for p in Pq])
+        want += ((Pq[:, 1] - 2.5)/np.where(Pq[:, 1] > 2.5, 0.2, 0.1))**2
+        np.testing.assert_allclose(got, want, rtol=R64)
