@@ -377,6 +377,9 @@ def run_ours(args):
                 if args.dtype == 'f64' else None,
                 'peak_source': 'measured live: mc3b_fma_peak register-resident FMA chains',
                 'ms_per_launch': kms,
+                'note': ('frac = SURVEY 8(d) algorithmic flops (10 per chain-point) over the measured FMA peak; '
+                         'this kernel executes %.2f FP64 instructions per chain-point, so frac may exceed 1 '
+                         '(fp64_pipe_frac is the executed-instruction view)' % pipe_instr),
                 'guard_hits': int(pop.guard_hits.item()) if moment else None,
                 'algorithmic_flops_per_chain_point': w['flops_per_point'],
                 'hbm_stream_GBs': 24.0*n/(kms*1e-3)/1e9,
