@@ -532,7 +532,7 @@ def _emit(line):
 def _profile_summary():
     """dram bytes per launch of the dominant kernel from the committed ncu capture."""
     try:
-        return json.load(open(os.path.join(ROOT, 'profiles', 'r2b_model_chisq.json')))
+        return json.load(open(os.path.join(ROOT, 'profiles', 'r2c_model_chisq.json')))
     except Exception:
         return {}
 
