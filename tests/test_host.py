@@ -209,3 +209,34 @@ def test_tile_layout_of_piecewise_uniform_abscissae():
     # many short runs: too much would be left over
     short = np.concatenate([i*5.0 + np.arange(150)*0.01 for i in range(40)])
     assert tile_layout(short) is None
+
+
+def test_tile_layout_invariants_on_random_gapped_series():
+    """Whatever the gaps, an accepted layout is a permutation, its tiles follow their own
+    origins to the kernel's tolerance, and nothing but tile points precedes the leftovers."""
+    from mc3_b200.gridseg import tile_layout, TILE
+    rs = np.random.RandomState(12)
+    accepted = 0
+    for trial in range(40):
+        n = int(rs.randint(600, 30000))
+        dx = 10.0**rs.uniform(-4, 1)
+        x = rs.uniform(-50, 50) + dx*np.arange(n)
+        keep = np.ones(n, bool)
+        for _ in range(rs.randint(0, 6)):
+            lo = rs.randint(0, n)
+            keep[lo:lo + rs.randint(1, max(2, n//10))] = False
+        x = x[keep]
+        if rs.rand() < 0.5 and x.size > 300:                     # the cadence resumes off the grid
+            x[x.size//2:] += rs.uniform(0, 1)*dx
+        L = tile_layout(x)
+        if L is None:
+            continue
+        accepted += 1
+        nt = L['starts'].size
+        assert np.array_equal(np.sort(L['perm']), np.arange(x.size))
+        assert L['perm'].size - nt*TILE == L['nleft'] <= max(64, int(0.02*x.size))
+        tiles = x[L['perm'][:nt*TILE]].reshape(nt, TILE)
+        tol = 8*np.finfo(float).eps*np.max(np.abs(x))
+        assert np.max(np.abs(tiles - (tiles[:, :1] + np.arange(TILE)*L['dx']))) <= tol
+        assert abs(L['dx'] - dx) <= 1e-12*dx
+    assert accepted >= 10
