@@ -57,6 +57,13 @@ int mc3b_device_sms(void);
  * Deterministic function of its arguments. */
 int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit);
 
+/* The same for a given kernel family: launches with opts.moment (the
+ * sufficient-statistics kernel) are planned with MC3B_PLAN_MOMENT, everything else
+ * with MC3B_PLAN_GENERAL (= mc3b_model_chisq_plan). */
+#define MC3B_PLAN_GENERAL 0
+#define MC3B_PLAN_MOMENT 1
+int mc3b_model_chisq_plan_kind(int kind, int64_t nchains, int64_t n, int dtype, int* nsplit);
+
 /* The split boundaries behind that plan, in data points: split s sums the points
  * [point_start[s], point_start[s+1]); point_start has nsplit+1 entries (HOST
  * memory, `cap` >= nsplit+1) and ends at n.  Large populations get splits of

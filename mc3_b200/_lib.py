@@ -73,6 +73,7 @@ _SIGS = {
     'mc3b_last_error': (ctypes.c_char_p, []),
     'mc3b_device_sms': (c_int, []),
     'mc3b_model_chisq_plan': (c_int, [c_i64, c_i64, c_int, ctypes.POINTER(c_int)]),
+    'mc3b_model_chisq_plan_kind': (c_int, [c_int, c_i64, c_i64, c_int, ctypes.POINTER(c_int)]),
     'mc3b_model_chisq_splits': (c_int, [c_i64, c_i64, c_int, ctypes.POINTER(c_i64), c_int,
                                         ctypes.POINTER(c_int)]),
     'mc3b_model_chisq': (c_int, [c_int, c_int, c_vp, c_i64, c_i64, c_int, c_vp,

@@ -221,9 +221,13 @@ struct Shape {
     int nsched; int32_t tstart[SCHED_MAX + 1];
 };
 
-Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
+// kind: MC3B_PLAN_GENERAL, or MC3B_PLAN_MOMENT for the sufficient-statistics kernel: it runs 4
+// CTAs per SM and its CTAs are short, so its waves are planned for 4 and its splits shrink
+// more slowly and stop at 8 tiles (measured at config 2: 0.0954 against 0.0985 ms; the same plan
+// costs the other kernels 3-16 %, profiles/r2_plan_ab.txt).
+Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms, int kind = MC3B_PLAN_GENERAL) {
     Shape s;
-    int RESIDENT = mc3b_chisq::RESIDENT;            // MC3B_PLAN_RESIDENT: experiments with other residencies
+    int RESIDENT = kind == MC3B_PLAN_MOMENT ? 4 : mc3b_chisq::RESIDENT;    // MC3B_PLAN_RESIDENT: experiments
     if (const char* e = getenv("MC3B_PLAN_RESIDENT")) RESIDENT = atoi(e) > 0 ? atoi(e) : RESIDENT;
     s.lc = nchains >= 96 ? 32 : (nchains >= 12 ? 8 : 1);
     const int tile = dtype == MC3B_F32 ? tilecfg<float>::TILE : tilecfg<double>::TILE;
@@ -245,7 +249,7 @@ Shape plan_shape(int64_t nchains, int64_t n, int dtype, int sms) {
     // ~one wave of splits takes 1/f of the tiles that remain.
     // f = 2, at least 4 tiles per split measured best at config 2 (0.203 -> 0.186 ms;
     // profiles/r1_split_schedule.md); MC3B_SCHED="f,min" overrides, "0" gives equal splits.
-    double f = 2.0; int mn = 4;
+    double f = kind == MC3B_PLAN_MOMENT ? 1.5 : 2.0; int mn = kind == MC3B_PLAN_MOMENT ? 8 : 4;
     if (const char* e = getenv("MC3B_SCHED")) { f = 0.0; sscanf(e, "%lf,%d", &f, &mn); }
     if (mn < 1) mn = 1;
     if (f >= 1.0 && s.lc == 32 && nfull < (1 << 30) && ns >= 8) {
@@ -291,7 +295,8 @@ int model_chisq_t(int model_id, const double* params, int64_t ldp, int64_t nchai
     const int64_t plan_chains = o.plan_chains > 0 ? o.plan_chains : nchains;
     MC3B_CHECK_ARG(plan_chains >= nchains, "plan_chains (%lld) is smaller than the launch (%lld chains)",
                    (long long)plan_chains, (long long)nchains);
-    const Shape sh = plan_shape(plan_chains, n, dtype, mc3b_sm_count());
+    const Shape sh = plan_shape(plan_chains, n, dtype, mc3b_sm_count(),
+                                o.moment != nullptr && usig ? MC3B_PLAN_MOMENT : MC3B_PLAN_GENERAL);
     A.nsched = sh.nsched;
     if (sh.nsched > 0) memcpy(A.tstart, sh.tstart, sizeof(int32_t) * (sh.nsched + 1));
     MC3B_CHECK_ARG(nsplit == sh.nsplit, "nsplit %d does not match the plan (%d)", nsplit, sh.nsplit);
@@ -412,13 +417,18 @@ __global__ void k_residuals(const double* model, const double* data, const doubl
 
 }  // namespace
 
-extern "C" int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit) {
+extern "C" int mc3b_model_chisq_plan_kind(int kind, int64_t nchains, int64_t n, int dtype, int* nsplit) {
     MC3B_CHECK_ARG(nchains > 0 && n > 0 && nsplit != nullptr, "bad plan arguments");
     MC3B_CHECK_ARG(dtype == MC3B_F64 || dtype == MC3B_F32, "bad dtype %d", dtype);
+    MC3B_CHECK_ARG(kind == MC3B_PLAN_GENERAL || kind == MC3B_PLAN_MOMENT, "bad plan kind %d", kind);
     int sms = mc3b_sm_count();
     if (sms <= 0) sms = 148;        // planning without a device (CPU-side sizing)
-    *nsplit = plan_shape(nchains, n, dtype, sms).nsplit;
+    *nsplit = plan_shape(nchains, n, dtype, sms, kind).nsplit;
     return MC3B_OK;
+}
+
+extern "C" int mc3b_model_chisq_plan(int64_t nchains, int64_t n, int dtype, int* nsplit) {
+    return mc3b_model_chisq_plan_kind(MC3B_PLAN_GENERAL, nchains, n, dtype, nsplit);
 }
 
 extern "C" int mc3b_model_chisq_splits(int64_t nchains, int64_t n, int dtype, int64_t* point_start, int cap,

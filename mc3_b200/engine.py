@@ -425,11 +425,12 @@ class Population:
             return nb
         return max(self.plan_chains, getattr(self, '_plan_rows', 0), nb)
 
-    def _plan(self, nb):
-        key = self._plan_chains(nb)
+    def _plan(self, nb, moment=False):
+        key = (self._plan_chains(nb), bool(moment))
         if key not in self._plans:
             ns = ctypes.c_int(0)
-            _lib.call('mc3b_model_chisq_plan', key, self.ndata, self.dtype, ctypes.byref(ns))
+            _lib.call('mc3b_model_chisq_plan_kind', 1 if moment else 0, key[0], self.ndata, self.dtype,
+                      ctypes.byref(ns))
             self._plans[key] = ns.value
         return self._plans[key]
 
@@ -516,8 +517,11 @@ class Population:
             self.launches += 2
             return out, nb, 1
         if self.kind == 'builtin':
-            ns = self._plan(nb)
+            moment = bool(getattr(self, 'use_moment', False)) and self.d_fold is not None \
+                and (fuse is not None or moment_ok)
+            ns = self._plan(nb, moment)
             part = self._workspace(('part', nb, ns), (ns, nb))
+            self._last_part = part
             o = _lib.ChisqOpts()
             o.plan_chains = self._plan_chains(nb) if self.plan_chains else 0
             o.uniform_sigma = 1 if self.usig else 0
@@ -526,7 +530,6 @@ class Population:
                 o.ntiles = self.seg['starts'].size
             if self.d_fold is not None:
                 o.folded = self.d_fold.data_ptr()
-                moment = self.use_moment and (fuse is not None or moment_ok)
                 if not os.environ.get('MC3B_NO_FOLD_CONSTS') or moment:
                     o.work = self._workspace(('foldk', nb), (_lib.FOLD_WORK, nb)).data_ptr()
                     self.launches += 1

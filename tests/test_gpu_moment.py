@@ -87,8 +87,7 @@ def _one_generation(pop, gen):
     before = pop.chisq_cur.clone()
     pop._generation(gen)
     torch.cuda.synchronize()
-    nb = pop.nlocal
-    part = [v for k, v in pop._work.items() if k[0] == 'part' and k[1] == nb][0]
+    part = pop._last_part
     return (pop.nextp.cpu().numpy(), part.sum(dim=0).cpu().numpy(), pop.inb.cpu().numpy() != 0,
             before.cpu().numpy(), pop.chisq_cur.cpu().numpy())
 
