@@ -240,3 +240,34 @@ def test_tile_layout_invariants_on_random_gapped_series():
         assert np.max(np.abs(tiles - (tiles[:, :1] + np.arange(TILE)*L['dx']))) <= tol
         assert abs(L['dx'] - dx) <= 1e-12*dx
     assert accepted >= 10
+
+
+def test_pair_and_moment_algebra_against_the_oracle():
+    """The two rearrangements of the uniform-grid sinusoid chi-squared the CUDA kernels use
+    (profiles/fold_error.py: mirrored pairs; profiles/moment_error.py: sufficient statistics
+    of those pairs), emulated in numpy with the kernels' operation order, against the
+    oracle's per-point chi-squared (src_c/_chisq.c:111-140 restated) -- no GPU involved."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles'))
+    import fold_error as fe
+    import moment_error as me
+    from oracle import kernels as ok, models as om
+    rs = np.random.RandomState(8)
+    n = 128*40
+    x = np.linspace(0.5, 9.5, n)
+    truth = np.array([1.0, 2.5, 0.3, 5.0, -0.2])
+    sigma = 0.5
+    d = om.sinusoid(truth, x) + rs.normal(0, sigma, n)
+    P = truth*(1 + 0.02*rs.standard_normal((24, 5)))
+    P[:4, 1] = 10**rs.uniform(-2.5, -1, 4)                       # a few samples per period
+    want = np.array([ok.chisq(om.sinusoid(p, x), d, np.full(n, sigma)) for p in P])
+    x0, dx = x[0], (x[-1] - x[0])/(n - 1)
+    pair = fe.folded_chisq(P, x0, dx, fe.fold(d), n)/sigma**2
+    np.testing.assert_allclose(pair, want, rtol=1e-12)
+    slr, c0r = np.polyfit(x, d, 1)
+    f, mom, D2 = me.prepare(d, x0, dx, c0r, slr)
+    mo = me.moment_chisq(P, x0, dx, f, mom, n, c0r, slr)/sigma**2
+    amp = me.amp_bound(P, n, x0, dx, D2, c0r, slr, want*sigma**2)
+    assert amp.max() < 4000                                       # the kernel's guard would pass them all
+    np.testing.assert_allclose(mo, want, rtol=1e-11)
